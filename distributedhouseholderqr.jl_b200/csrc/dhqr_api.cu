@@ -1,0 +1,748 @@
+// dhqr_api.cu — context, workspace, panel/update drivers and the C-ABI of libdhqr.so.
+// See include/dhqr.h for the contract; each entry point names the reference method it replaces
+// (S:n = /root/reference/src/DistributedHouseholderQR.jl:n).
+#include "../../include/dhqr.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dhqr_kernels.cuh"
+
+using namespace dhqr;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return set_err(1000 + (int)e_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(call)          \
+    do {                   \
+        int rc_ = (call);  \
+        if (rc_) return rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use needs no NCCL at all
+// ------------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclInt64 = 4, ncclSum = 0 };
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    // An already-loaded libnccl.so.2 (e.g. the one bundled with torch) is reused by soname.
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return set_err(2001, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                       \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                        \
+    if (!g_nccl.field) return set_err(2002, "libnccl lacks symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(AllGather, "ncclAllGather")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != 0) return set_err(3000 + (int)r_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct dhqr_context {
+    int device = 0, sms = 0;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    // options
+    int nb = 128, panel_ctas = 0, sync = 0;
+    // workspace
+    double* vbuf = nullptr;  size_t vbuf_elems = 0;  int64_t ldv = 0;   // packed V block  [NBMAX][ldv]
+    double* wpart = nullptr; size_t wpart_elems = 0;                    // gemm_vta partials
+    double* ybuf = nullptr;  size_t ybuf_elems = 0;                     // Y = -T'W
+    double* linv = nullptr;                                             // [128*128]
+    double* ppart = nullptr; size_t ppart_elems = 0;                    // panel partials [2][G][IB]
+    double* ppiv = nullptr;                                             // [2][IB]
+    double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
+    double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
+    double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
+    double* hostB = nullptr; size_t hostB_elems = 0;
+    int64_t* d_i64 = nullptr;                                           // small int64 scratch (partition exchange)
+    unsigned long long* bar = nullptr;
+    unsigned long long bar_count = 0;
+    int64_t launches = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // kernel attribute state
+    bool attrs_set = false;
+};
+
+static constexpr int NBMAX = 128;
+static constexpr int MAXCTAS_FACTOR = 3;
+
+// gemm tile configurations
+static constexpr int G1_BN = 64, G1_STAGES = 4;             // gemm_vta<128>: 128 x 64 tile, 8+1 warps
+static constexpr int G1S_BN = 128, G1S_STAGES = 4;          // gemm_vta<32> : 32 x 128 tile, 4+1 warps
+static constexpr int G2_BM = 128, G2_BN = 64, G2_STAGES = 2;  // gemm_cvy: 128 x 64 tile, 4+1 warps, 2 CTAs/SM
+
+static size_t smem_g1(int nbp, int bn, int stages) { return (size_t)stages * (nbp + bn) * LDK * 8 + 2 * stages * 8; }
+static size_t smem_g2() { return (size_t)G2_STAGES * (KC * (G2_BM + 4) + G2_BN * LDK) * 8 + 2 * G2_STAGES * 8; }
+static size_t smem_tinv(int nbp) { return ((size_t)nbp * (nbp + 1) + 4 * 32 * 33) * 8; }
+static size_t smem_ymake(int nbp) { return ((size_t)nbp * nbp + YCOLS * nbp) * 8; }
+
+#define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_STAGES>
+#define K_G1_32 k_gemm_vta<32, G1S_BN, 1, 4, G1S_STAGES>
+#define K_G2 k_gemm_cvy<G2_BM, G2_BN, 2, 2, G2_STAGES, 2>
+
+static int set_attrs(dhqr_context* c) {
+    if (c->attrs_set) return 0;
+    CU(cudaFuncSetAttribute(K_G1_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(128, G1_BN, G1_STAGES)));
+    CU(cudaFuncSetAttribute(K_G1_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(32, G1S_BN, G1S_STAGES)));
+    CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
+    CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
+    CU(cudaFuncSetAttribute(k_tinv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(32)));
+    CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
+    CU(cudaFuncSetAttribute(k_ymake<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(32)));
+    CU(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->attrs_set = true;
+    return 0;
+}
+
+template <typename T>
+static int ensure(T** p, size_t* have, size_t need) {
+    if (*have >= need && *p) return 0;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    CU(cudaMalloc((void**)p, need * sizeof(T)));
+    CU(cudaMemset(*p, 0, need * sizeof(T)));
+    *have = need;
+    return 0;
+}
+
+static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
+    TRY(set_attrs(c));
+    const int64_t ldv = rup(m, 128) + 128;
+    if (c->ldv < ldv || !c->vbuf) {
+        TRY(ensure(&c->vbuf, &c->vbuf_elems, (size_t)ldv * NBMAX));
+        c->ldv = ldv;
+    }
+    const int64_t maxctas = (int64_t)MAXCTAS_FACTOR * c->sms;
+    const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
+    TRY(ensure(&c->wpart, &c->wpart_elems, (size_t)std::max(maxctas, tiles_max) * NBMAX * G1S_BN + (size_t)NBMAX * G1S_BN));
+    TRY(ensure(&c->ybuf, &c->ybuf_elems, (size_t)NBMAX * (rup(n_local_max, 128) + 128)));
+    size_t one = 0;
+    if (!c->linv) { one = 0; TRY(ensure(&c->linv, &one, (size_t)NBMAX * NBMAX)); }
+    TRY(ensure(&c->ppart, &c->ppart_elems, (size_t)2 * c->sms * IB));
+    if (!c->ppiv) { one = 0; TRY(ensure(&c->ppiv, &one, (size_t)2 * IB)); }
+    TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
+    TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
+    return 0;
+}
+
+static int post(dhqr_context* c, cudaStream_t st, const char* what) {
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(1000 + (int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    if (c->sync) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return set_err(1000 + (int)e, "%s failed: %s", what, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-reflector application  C <- (I - V T' V') C  on window rows >= row_lo
+//   V: nbp columns of the packed V buffer starting at Vcols (window row 0), T from the Gram matrix.
+// ------------------------------------------------------------------------------------------------
+static int pick_splits(int tiles, int nchunks, int sms) {
+    int smax = std::max(1, std::min(nchunks / 4, (MAXCTAS_FACTOR * sms) / std::max(tiles, 1)));
+    int best = 1;
+    double beste = 0.0;
+    for (int s = 1; s <= smax; ++s) {
+        const int ctas = tiles * s;
+        const double e = (double)ctas / ((double)sms * ((ctas + sms - 1) / sms));
+        if (e > beste + 1e-9) { beste = e; best = s; }
+    }
+    return best;
+}
+
+static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* Vcols, int nbp, int64_t rows,
+                                 int64_t row_lo, double* C, int64_t ldc, int ncols) {
+    if (ncols <= 0 || rows <= 0) return 0;
+    const bool small = (nbp <= 32);
+    const int NBPK = small ? 32 : 128;          // kernel instantiation (V columns beyond nbp are zero)
+    const int bn = small ? G1S_BN : G1_BN;
+    const int next = NBPK + ncols;
+    const int tiles = (next + bn - 1) / bn;
+    const int nchunks = (int)((rows + KC - 1) / KC);
+    const int nsplit = pick_splits(tiles, nchunks, c->sms);
+    const int64_t pstride = (int64_t)tiles * bn * NBPK;
+    if ((size_t)(pstride * nsplit) > c->wpart_elems) return set_err(4001, "internal: W partial workspace too small");
+    GemmVtaArgs g1;
+    g1.V = Vcols; g1.ldv = c->ldv; g1.nv = NBPK;
+    g1.A = C; g1.lda = ldc; g1.rows = rows; g1.na = ncols; g1.nchunks = nchunks;
+    g1.a_aligned = (((uintptr_t)C & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
+    g1.Wp = c->wpart; g1.pstride = pstride;
+    dim3 grid1(tiles, nsplit);
+    if (small) {
+        K_G1_32<<<grid1, (1 * 4 + 1) * 32, smem_g1(32, G1S_BN, G1S_STAGES), st>>>(g1);
+    } else {
+        K_G1_128<<<grid1, (4 * 2 + 1) * 32, smem_g1(128, G1_BN, G1_STAGES), st>>>(g1);
+    }
+    TRY(post(c, st, "k_gemm_vta"));
+    if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(c->wpart, pstride, nsplit, c->linv);
+    else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(c->wpart, pstride, nsplit, c->linv);
+    TRY(post(c, st, "k_tinv"));
+    const int ygrid = (ncols + YCOLS - 1) / YCOLS;
+    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
+    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
+    TRY(post(c, st, "k_ymake"));
+    GemmCvyArgs g2;
+    g2.C = C; g2.ldc = ldc; g2.rows = rows; g2.row_lo = row_lo; g2.ncols = ncols;
+    g2.V = Vcols; g2.ldv = c->ldv; g2.Y = c->ybuf; g2.ldy = NBPK; g2.nbp = small ? 32 : (int)rup(nbp, KC);
+    dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
+    K_G2<<<grid2, (2 * 2 + 1) * 32, smem_g2(), st>>>(g2);
+    TRY(post(c, st, "k_gemm_cvy"));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cooperative panel launch: factor mp x ncols (<= IB) at P, V block -> vout columns
+// ------------------------------------------------------------------------------------------------
+static int launch_panel(dhqr_context* c, cudaStream_t st, double* P, int64_t ldp, int64_t mp, int ncols, double* alpha,
+                        double* vout, int64_t vtop, int64_t vrows) {
+    int gmax = c->panel_ctas > 0 ? std::min(c->panel_ctas, c->sms) : c->sms;
+    int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
+    rpc = rup(rpc, 8);
+    const int G = (int)((mp + rpc - 1) / rpc);
+    const int lds = (int)rpc | 1;
+    const size_t smem = (size_t)IB * lds * 8;
+    if (smem > 200 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
+    if ((size_t)2 * G * IB > c->ppart_elems) return set_err(4002, "internal: panel partial workspace too small");
+    PanelArgs a;
+    a.P = P; a.ldp = ldp; a.mp = mp; a.ncols = ncols; a.alpha = alpha;
+    a.Vout = vout; a.ldv = c->ldv; a.vtop = vtop; a.vrows = vrows;
+    a.rows_per_cta = (int)rpc; a.lds = lds;
+    a.part = c->ppart; a.piv = c->ppiv; a.bar = c->bar; a.bar_base = c->bar_count;
+    void* args[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
+    if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_panel failed: %s", cudaGetErrorString(e));
+    c->bar_count += (unsigned long long)G * ncols;
+    return post(c, st, "k_panel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// partition bookkeeping: global list of panels (owner, first global column, width)
+// ------------------------------------------------------------------------------------------------
+struct Panel { int owner; int64_t c; int kb; };
+
+static int gather_partition(dhqr_context* c, cudaStream_t st, int64_t col0, int64_t n_local, std::vector<int64_t>& col0s,
+                            std::vector<int64_t>& nls) {
+    col0s.assign(c->nranks, 0);
+    nls.assign(c->nranks, 0);
+    if (c->nranks == 1) { col0s[0] = col0; nls[0] = n_local; return 0; }
+    int64_t mine[2] = {col0, n_local};
+    CU(cudaMemcpyAsync(c->d_i64, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    NC(g_nccl.AllGather(c->d_i64, c->d_i64 + 2, 2, ncclInt64, c->comm, st));
+    std::vector<int64_t> all(2 * c->nranks);
+    CU(cudaMemcpyAsync(all.data(), c->d_i64 + 2, sizeof(int64_t) * 2 * c->nranks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < c->nranks; ++r) { col0s[r] = all[2 * r]; nls[r] = all[2 * r + 1]; }
+    return 0;
+}
+
+static int check_partition(const std::vector<int64_t>& col0s, const std::vector<int64_t>& nls, int64_t n_global) {
+    // DArray (1,P) grid: contiguous, ascending with rank (S:19, test/runtests.jl:71)
+    int64_t next = 0;
+    for (size_t r = 0; r < col0s.size(); ++r) {
+        if (col0s[r] != next || nls[r] < 0) return set_err(-4, "column blocks must be contiguous and ascending with rank (rank %zu: col0=%lld, expected %lld)", r, (long long)col0s[r], (long long)next);
+        next += nls[r];
+    }
+    if (next != n_global) return set_err(-3, "column blocks cover %lld columns, n_global=%lld", (long long)next, (long long)n_global);
+    return 0;
+}
+
+static void build_panels(const std::vector<int64_t>& col0s, const std::vector<int64_t>& nls, int nb, std::vector<Panel>& out) {
+    out.clear();
+    for (size_t r = 0; r < col0s.size(); ++r)
+        for (int64_t o = 0; o < nls[r]; o += nb) out.push_back({(int)r, col0s[r] + o, (int)std::min<int64_t>(nb, nls[r] - o)});
+}
+
+static int check_common(dhqr_context* c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const void* A, int64_t lda) {
+    if (!c) return set_err(-1, "null handle");
+    if (m < 0) return set_err(-2, "m < 0");
+    if (n_global < 0 || n_global > m) return set_err(-3, "need 0 <= n_global <= m (reference asserts full column rank shapes)");
+    if (col0 < 0 || col0 > n_global) return set_err(-4, "col0 out of range");
+    if (n_local < 0 || col0 + n_local > n_global) return set_err(-5, "n_local out of range");
+    if (n_local > 0 && !A) return set_err(-6, "null matrix pointer");
+    if (lda < std::max<int64_t>(1, m)) return set_err(-7, "lda < max(1,m)");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// qr!: blocked driver  (S:113-148, S:198-213)
+// ------------------------------------------------------------------------------------------------
+static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, int64_t col0, int64_t nl, double* A,
+                      int64_t lda, double* alpha, int nb) {
+    std::vector<int64_t> col0s, nls;
+    TRY(gather_partition(c, st, col0, nl, col0s, nls));
+    TRY(check_partition(col0s, nls, n));
+    int64_t nlmax = 0;
+    for (auto v : nls) nlmax = std::max(nlmax, v);
+    TRY(ensure_workspace(c, m, nlmax));
+    std::vector<Panel> panels;
+    build_panels(col0s, nls, nb, panels);
+    const int64_t lend = col0 + nl;
+    for (const Panel& p : panels) {
+        const int64_t r0 = p.c & ~(int64_t)31;             // window start: 32-row aligned for the TMA chunks
+        const int64_t rows = m - r0;                        // valid window rows
+        const int64_t vrows = rup(rows, 128);
+        const int nbp = (int)rup(p.kb, IB);
+        if (c->rank == p.owner) {
+            for (int o = 0; o < p.kb; o += IB) {
+                const int ib = std::min(IB, p.kb - o);
+                const int64_t cs = p.c + o;                                   // global column == pivot row
+                double* P = A + (cs - col0) * lda + cs;
+                TRY(launch_panel(c, st, P, lda, m - cs, ib, alpha + cs, c->vbuf + (int64_t)o * c->ldv, cs - r0, vrows));
+                const int rem = p.kb - (o + ib);
+                if (rem > 0)   // update the rest of the outer panel with this sub-panel's reflectors
+                    TRY(apply_block_reflector(c, st, c->vbuf + (int64_t)o * c->ldv, IB, rows, cs - r0,
+                                              A + (cs + ib - col0) * lda + r0, lda, rem));
+            }
+            if (nbp > IB && nbp < NBMAX)   // zero the V columns the 128-wide kernels read beyond nbp
+                CU(cudaMemsetAsync(c->vbuf + (int64_t)nbp * c->ldv, 0, sizeof(double) * (size_t)(NBMAX - nbp) * c->ldv, st));
+        }
+        if (c->nranks > 1) {
+            // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
+            NC(g_nccl.Broadcast(c->vbuf, c->vbuf, (size_t)c->ldv * (nbp > IB ? NBMAX : IB), ncclFloat64, p.owner, c->comm, st));
+            NC(g_nccl.Broadcast(alpha + p.c, alpha + p.c, (size_t)p.kb, ncclFloat64, p.owner, c->comm, st));
+        }
+        // trailing update of the local columns right of the panel (S:198-213 for nb columns at once)
+        const int64_t t0 = std::max(p.c + p.kb, col0);
+        if (t0 < lend)
+            TRY(apply_block_reflector(c, st, c->vbuf, nbp, rows, p.c - r0, A + (t0 - col0) * lda + r0, lda, (int)(lend - t0)));
+    }
+    return 0;
+}
+
+// qr!: unblocked driver (nb == 1): one reflector per step, as the reference does it (S:127-144)
+static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, int64_t col0, int64_t nl, double* A,
+                        int64_t lda, double* alpha) {
+    std::vector<int64_t> col0s, nls;
+    TRY(gather_partition(c, st, col0, nl, col0s, nls));
+    TRY(check_partition(col0s, nls, n));
+    TRY(ensure_workspace(c, m, nl));
+    const int64_t lend = col0 + nl;
+    for (int owner = 0; owner < c->nranks; ++owner) {
+        for (int64_t j = col0s[owner]; j < col0s[owner] + nls[owner]; ++j) {
+            const int lead = (int)(j & 1);          // window starts on an even row so TMA sources stay 16B aligned
+            const int64_t len = m - j;
+            if (c->rank == owner) {
+                if (lead) CU(cudaMemsetAsync(c->v1, 0, sizeof(double), st));
+                k_house1<<<1, 1024, 0, st>>>(A + (j - col0) * lda + j, len, alpha + j, c->v1 + lead);
+                TRY(post(c, st, "k_house1"));
+            }
+            if (c->nranks > 1) {
+                NC(g_nccl.Broadcast(c->v1, c->v1, (size_t)(len + lead + 1), ncclFloat64, owner, c->comm, st));
+                NC(g_nccl.Broadcast(alpha + j, alpha + j, 1, ncclFloat64, owner, c->comm, st));
+            }
+            const int64_t t0 = std::max(j + 1, col0);
+            if (t0 >= lend) continue;
+            const int nc = (int)(lend - t0);
+            double* C = A + (t0 - col0) * lda + (j - lead);
+            const int64_t lenw = len + lead;
+            const int64_t lenp = (lenw + 1) & ~(int64_t)1;
+            const size_t smem = (size_t)lenp * 8 * (A1_CW + 1);
+            if (smem <= 200 * 1024) {
+                const int aligned = (((uintptr_t)C & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+                k_apply1_tma<<<(nc + A1_CW - 1) / A1_CW, A1_THREADS, smem, st>>>(c->v1, lenw, C, lda, nc, aligned);
+                TRY(post(c, st, "k_apply1_tma"));
+            } else {
+                k_apply1_direct<<<std::min(nc, 8 * c->sms), A1_THREADS, 0, st>>>(c->v1, lenw, C, lda, nc);
+                TRY(post(c, st, "k_apply1_direct"));
+            }
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve phases
+// ------------------------------------------------------------------------------------------------
+// Q'b on the local reflectors: panels of <= 128 reflectors, each applied as a block reflector
+// built from V alone (T recomputed from V'V), so only (A, alpha) are needed, like the reference.
+static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, const double* A,
+                          int64_t lda, double* b, int64_t ldb, int nrhs) {
+    for (int64_t o = 0; o < nl; o += NBMAX) {
+        const int kb = (int)std::min<int64_t>(NBMAX, nl - o);
+        const int64_t cs = col0 + o;
+        const int64_t r0 = cs & ~(int64_t)31;
+        const int64_t rows = m - r0, vrows = rup(rows, 128);
+        const int nbp = kb <= IB ? IB : NBMAX;
+        dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbp);
+        k_pack_v<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, c->vbuf, c->ldv, cs - r0, vrows, nbp);
+        TRY(post(c, st, "k_pack_v"));
+        TRY(apply_block_reflector(c, st, c->vbuf, nbp, rows, cs - r0, b + r0, ldb, nrhs));
+    }
+    return 0;
+}
+
+static int backsolve_local(dhqr_context* c, cudaStream_t st, int64_t col0, int64_t nl, const double* A, int64_t lda,
+                           const double* alpha, double* y, int64_t ldy, int nrhs, double* x, int64_t ldx) {
+    // blocks of BS_BLK columns, last to first (S:260: i = n:-1:1)
+    if (nl <= 0) return 0;
+    for (int64_t o = ((nl - 1) / BS_BLK) * BS_BLK; o >= 0; o -= BS_BLK) {
+        const int bs = (int)std::min<int64_t>(BS_BLK, nl - o);
+        const int64_t c0 = col0 + o;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((c0 + 255) / 256, 2 * c->sms));
+        k_backsolve_step<<<grid, 256, 0, st>>>(A + o * lda, lda, alpha, y, ldy, nrhs, x, ldx, c0, bs);
+        TRY(post(c, st, "k_backsolve_step"));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dhqr_version(void) { return DHQR_VERSION; }
+const char* dhqr_last_error(void) { return g_err; }
+
+static int create_common(dhqr_handle* h, int device) {
+    if (!h) return set_err(-1, "null handle pointer");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_err(-2, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return set_err(5001, "libdhqr is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    dhqr_context* c = new dhqr_context();
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    CU(cudaMalloc((void**)&c->bar, 64));
+    CU(cudaMemset(c->bar, 0, 64));
+    CU(cudaMalloc((void**)&c->d_i64, sizeof(int64_t) * 2 * 1025));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev0, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev1, cudaEventDisableTiming));
+    *h = c;
+    return 0;
+}
+
+int dhqr_create(dhqr_handle* h, int device) { return create_common(h, device); }
+
+int dhqr_nccl_unique_id(void* out) {
+    if (!out) return set_err(-1, "null output");
+    TRY(load_nccl());
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+int dhqr_create_dist(dhqr_handle* h, int device, const void* unique_id, int rank, int nranks) {
+    if (nranks < 1 || nranks > 1024) return set_err(-5, "nranks out of range");
+    if (rank < 0 || rank >= nranks) return set_err(-4, "rank out of range");
+    if (nranks > 1 && !unique_id) return set_err(-3, "null unique id");
+    TRY(create_common(h, device));
+    dhqr_context* c = *h;
+    c->rank = rank;
+    c->nranks = nranks;
+    if (nranks > 1) {
+        TRY(load_nccl());
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof(id));
+        NC(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    }
+    return 0;
+}
+
+int dhqr_destroy(dhqr_handle c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->vbuf); cudaFree(c->wpart); cudaFree(c->ybuf); cudaFree(c->linv); cudaFree(c->ppart); cudaFree(c->ppiv);
+    cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64); cudaFree(c->bar);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return 0;
+}
+
+int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
+    if (!c) return set_err(-1, "null handle");
+    if (!key) return set_err(-2, "null key");
+    if (!strcmp(key, "nb")) {
+        if (value < 32 || value > 128 || value % 32) return set_err(-3, "nb must be a multiple of 32 in [32,128]");
+        c->nb = (int)value;
+    } else if (!strcmp(key, "panel_ctas")) {
+        if (value < 0) return set_err(-3, "panel_ctas < 0");
+        c->panel_ctas = (int)value;
+    } else if (!strcmp(key, "sync")) {
+        c->sync = value ? 1 : 0;
+    } else {
+        return set_err(-2, "unknown option '%s'", key);
+    }
+    return 0;
+}
+
+int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
+    if (!c) return set_err(-1, "null handle");
+    if (!key) return set_err(-2, "null key");
+    if (!value) return set_err(-3, "null value");
+    if (!strcmp(key, "nb")) *value = c->nb;
+    else if (!strcmp(key, "panel_ctas")) *value = c->panel_ctas;
+    else if (!strcmp(key, "sync")) *value = c->sync;
+    else if (!strcmp(key, "sms")) *value = c->sms;
+    else if (!strcmp(key, "rank")) *value = c->rank;
+    else if (!strcmp(key, "nranks")) *value = c->nranks;
+    else return set_err(-2, "unknown option '%s'", key);
+    return 0;
+}
+
+int dhqr_launch_count(dhqr_handle c, int64_t* count) {
+    if (!c) return set_err(-1, "null handle");
+    if (!count) return set_err(-2, "null count");
+    *count = c->launches;
+    return 0;
+}
+
+int dhqr_qr_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, double* dA, int64_t lda,
+                double* d_alpha, int nb, void* stream) {
+    TRY(check_common(c, m, n_global, col0, n_local, dA, lda));
+    if (n_global > 0 && !d_alpha) return set_err(-8, "null alpha");
+    if (nb == 0) nb = c->nb;
+    if (nb != 1 && (nb < 32 || nb > 128 || nb % 32)) return set_err(-9, "nb must be 0, 1 or a multiple of 32 in [32,128]");
+    if (n_global == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb == 1) return qr_unblocked(c, st, m, n_global, col0, n_local, dA, lda, d_alpha);
+    return qr_blocked(c, st, m, n_global, col0, n_local, dA, lda, d_alpha, nb);
+}
+
+int dhqr_apply_qt_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const double* dA,
+                      int64_t lda, double* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(check_common(c, m, n_global, col0, n_local, dA, lda));
+    if (nrhs < 0) return set_err(-10, "nrhs < 0");
+    if (nrhs > 0 && !d_b) return set_err(-8, "null b");
+    if (ldb < std::max<int64_t>(1, m)) return set_err(-9, "ldb < max(1,m)");
+    if (n_global == 0 || nrhs == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> col0s, nls;
+    TRY(gather_partition(c, st, col0, n_local, col0s, nls));
+    TRY(check_partition(col0s, nls, n_global));
+    TRY(ensure_workspace(c, m, std::max<int64_t>(n_local, nrhs)));
+    // C3 (S:227-229): owners act on b one after the other; b travels rank -> rank
+    const size_t cnt = (size_t)ldb * (nrhs - 1) + m;
+    if (c->nranks > 1 && c->rank > 0) NC(g_nccl.Recv(d_b, cnt, ncclFloat64, c->rank - 1, c->comm, st));
+    TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs));
+    if (c->nranks > 1) {
+        if (c->rank + 1 < c->nranks) NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
+        NC(g_nccl.Broadcast(d_b, d_b, cnt, ncclFloat64, c->nranks - 1, c->comm, st));
+    }
+    return 0;
+}
+
+int dhqr_backsolve_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const double* dA,
+                       int64_t lda, const double* d_alpha, double* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(check_common(c, m, n_global, col0, n_local, dA, lda));
+    if (n_global > 0 && !d_alpha) return set_err(-8, "null alpha");
+    if (nrhs < 0) return set_err(-11, "nrhs < 0");
+    if (nrhs > 0 && !d_b) return set_err(-9, "null b");
+    if (ldb < std::max<int64_t>(1, m)) return set_err(-10, "ldb < max(1,m)");
+    if (n_global == 0 || nrhs == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> col0s, nls;
+    TRY(gather_partition(c, st, col0, n_local, col0s, nls));
+    TRY(check_partition(col0s, nls, n_global));
+    TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)n_global * nrhs));
+    // C4 (S:260-267), column oriented: the last owner solves its block of unknowns and removes their
+    // contribution from the rows above; the partially reduced right-hand side then moves one rank down.
+    const size_t cnt = (size_t)ldb * (nrhs - 1) + n_global;
+    if (c->nranks > 1 && c->rank + 1 < c->nranks) {
+        NC(g_nccl.Recv(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
+        NC(g_nccl.Recv(c->xbuf, (size_t)n_global * nrhs, ncclFloat64, c->rank + 1, c->comm, st));
+    }
+    TRY(backsolve_local(c, st, col0, n_local, dA, lda, d_alpha, d_b, ldb, nrhs, c->xbuf, n_global));
+    if (c->nranks > 1) {
+        if (c->rank > 0) {
+            NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank - 1, c->comm, st));
+            NC(g_nccl.Send(c->xbuf, (size_t)n_global * nrhs, ncclFloat64, c->rank - 1, c->comm, st));
+        }
+        NC(g_nccl.Broadcast(c->xbuf, c->xbuf, (size_t)n_global * nrhs, ncclFloat64, 0, c->comm, st));
+    }
+    CU(cudaMemcpy2DAsync(d_b, (size_t)ldb * 8, c->xbuf, (size_t)n_global * 8, (size_t)n_global * 8, nrhs,
+                         cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dhqr_solve_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const double* dA,
+                   int64_t lda, const double* d_alpha, double* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(dhqr_apply_qt_f64(c, m, n_global, col0, n_local, dA, lda, d_b, ldb, nrhs, stream));   // S:288
+    return dhqr_backsolve_f64(c, m, n_global, col0, n_local, dA, lda, d_alpha, d_b, ldb, nrhs, stream);   // S:291
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t lda, double* h_alpha, int nb) {
+    TRY(check_common(c, m, n, 0, n, hA, lda));
+    if (n > 0 && !h_alpha) return set_err(-6, "null alpha");
+    if (c->nranks != 1) return set_err(-1, "host entry points are single-GPU");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const int64_t ldd = rup(m, 32);                       // padded device leading dimension (aligned TMA sources)
+    TRY(ensure(&c->hostA, &c->hostA_elems, (size_t)ldd * n + (size_t)n));
+    double* dA = c->hostA;
+    double* dal = c->hostA + (size_t)ldd * n;
+    cudaStream_t st = c->copy_stream;
+    CU(cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+    TRY(dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st));
+    CU(cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int dhqr_ldiv_host_f64(dhqr_handle c, int64_t m, int64_t n, const double* hA, int64_t lda, const double* h_alpha,
+                       const double* h_b, double* h_x) {
+    TRY(check_common(c, m, n, 0, n, hA, lda));
+    if (n > 0 && !h_alpha) return set_err(-6, "null alpha");
+    if (m > 0 && !h_b) return set_err(-7, "null b");
+    if (n > 0 && !h_x) return set_err(-8, "null x");
+    if (c->nranks != 1) return set_err(-1, "host entry points are single-GPU");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const int64_t ldd = rup(m, 32);
+    TRY(ensure(&c->hostA, &c->hostA_elems, (size_t)ldd * n + (size_t)n));
+    TRY(ensure(&c->hostB, &c->hostB_elems, (size_t)ldd));
+    double* dA = c->hostA;
+    double* dal = c->hostA + (size_t)ldd * n;
+    cudaStream_t st = c->copy_stream;
+    CU(cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dal, h_alpha, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->hostB, h_b, (size_t)m * 8, cudaMemcpyHostToDevice, st));   // S:318: b itself is never touched
+    TRY(dhqr_solve_f64(c, m, n, 0, n, dA, ldd, dal, c->hostB, ldd, 1, st));
+    CU(cudaMemcpyAsync(h_x, c->hostB, (size_t)n * 8, cudaMemcpyDeviceToHost, st));     // S:320
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- primitives ---------------------------------------------------------------------------------
+int dhqr_partialdot_f64(dhqr_handle c, const double* d_a, const double* d_b, int64_t i0, int64_t i1, double* d_out,
+                        void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (!d_a) return set_err(-2, "null a");
+    if (!d_b) return set_err(-3, "null b");
+    if (i0 < 0) return set_err(-4, "i0 < 0");
+    if (i1 < i0) return set_err(-5, "i1 < i0");
+    if (!d_out) return set_err(-6, "null out");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_partialdot<<<1, 1024, 0, st>>>(d_a, d_b, i0, i1, d_out);
+    return post(c, st, "k_partialdot");
+}
+
+int dhqr_fill_uniform_f64(dhqr_handle c, uint64_t seed, int64_t i0, int64_t j0, int64_t m, int64_t n, double* dA,
+                          int64_t lda, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (m < 0) return set_err(-5, "m < 0");
+    if (n < 0) return set_err(-6, "n < 0");
+    if (m == 0 || n == 0) return 0;
+    if (!dA) return set_err(-7, "null matrix");
+    if (lda < m) return set_err(-8, "lda < m");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)std::min<int64_t>((m + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 4096));
+    k_fill_uniform<<<grid, 256, 0, st>>>(seed, i0, j0, m, n, dA, lda);
+    return post(c, st, "k_fill_uniform");
+}
+
+// ---- kernel-level hooks ---------------------------------------------------------------------------
+int dhqr_k_block_reflector_f64(dhqr_handle c, int64_t rows, int nbp, const double* dV, int64_t ldv, int64_t row_lo,
+                               int ncols, double* dC, int64_t ldc, double* d_linv_out, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (rows <= 0) return set_err(-2, "rows <= 0");
+    if (nbp < 1 || nbp > 128) return set_err(-3, "nbp out of range");
+    if (!dV) return set_err(-4, "null V");
+    if (ldv < rows) return set_err(-5, "ldv < rows");
+    if (!dC) return set_err(-8, "null C");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(c, rows, ncols));
+    const int nbk = nbp <= IB ? IB : NBMAX;
+    CU(cudaMemsetAsync(c->vbuf, 0, sizeof(double) * (size_t)c->ldv * nbk, st));
+    CU(cudaMemcpy2DAsync(c->vbuf, (size_t)c->ldv * 8, dV, (size_t)ldv * 8, (size_t)rows * 8, (size_t)nbp,
+                         cudaMemcpyDeviceToDevice, st));
+    TRY(apply_block_reflector(c, st, c->vbuf, nbk, rows, row_lo, dC, ldc, ncols));
+    if (d_linv_out) CU(cudaMemcpyAsync(d_linv_out, c->linv, sizeof(double) * (size_t)nbk * nbk, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dhqr_k_panel_f64(dhqr_handle c, int64_t rows, int ncols, double* dP, int64_t ldp, double* d_alpha, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (rows <= 0) return set_err(-2, "rows <= 0");
+    if (ncols < 1 || ncols > IB || ncols > rows) return set_err(-3, "ncols out of range");
+    if (!dP) return set_err(-4, "null panel");
+    if (ldp < rows) return set_err(-5, "ldp < rows");
+    if (!d_alpha) return set_err(-6, "null alpha");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(c, rows, ncols));
+    return launch_panel(c, st, dP, ldp, rows, ncols, d_alpha, c->vbuf, 0, rup(rows, 128));
+}
+
+}  // extern "C"

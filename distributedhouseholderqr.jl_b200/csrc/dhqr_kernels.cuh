@@ -1,0 +1,800 @@
+// dhqr_kernels.cuh — hand-written sm_100a kernels for the blocked Householder QR hot path.
+//
+// Reference semantics (S:n = /root/reference/src/DistributedHouseholderQR.jl:n):
+//   column step      S:127-135   s=|x|, alpha=-sign(x1)s, f=1/sqrt(s(s+|x1|)), v=f(x-alpha e1), |v|^2=2
+//   trailing update  S:198-213   a <- a - v (v'a)      (partialdot S:42-49, hotloop! S:156-160)
+//   Q'b sweep        S:232-242
+//   back-substitute  S:256-282
+// The kernels here compute the same reflectors, but blocked: nb reflectors are aggregated into
+//   Q_panel' = I - V T' V',  T^{-1} = I + striu(V'V)        (beta == 1 because |v|^2 == 2)
+// so that the trailing update is two dense fp64 GEMMs on the tensor pipe (DMMA; tcgen05 has no
+// f64 kind), fed by TMA bulk copies (cp.async.bulk -> UBLKCP) through an mbarrier ring.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dhqr {
+
+constexpr int KC = 32;        // K-chunk: rows per stage in gemm_vta, V columns per stage in gemm_cvy
+constexpr int LDK = KC + 4;   // padded leading dim of [column][k] smem tiles: 36 doubles (288 B), 36 % 16 == 4
+constexpr int IB = 32;        // inner (cooperative) panel width
+constexpr int PANEL_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, TMA bulk copy, fp64 tensor-core MMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor pipe (SASS: DMMA.8x8x4).
+//   a : A[lane>>2][lane&3]      b : B[lane&3][lane>>2]      c0,c1 : C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_vta:  Wext(NBP x next) = V' * [V(:,0:nv) | A]      "TN", reduction over the long row dimension
+//   V   : ldv x NBP packed Householder block (rows = window rows, zero above the diagonal and in
+//         the padding rows), always full KC-row chunks.
+//   A   : trailing columns (user storage), `rows` valid rows; the last chunk may be ragged.
+//   grid: (tiles over ext columns, splits over row chunks); each CTA writes one partial tile to
+//         Wp[split]; ymake/tinv sum the partials in a fixed order (deterministic).
+//   CTA : WM*WN consumer warps (32x32 warp tiles of 8x8x4 DMMAs) + 1 TMA producer warp.
+// ------------------------------------------------------------------------------------------------
+struct GemmVtaArgs {
+    const double* V;    // window row 0, first V column of this block
+    int64_t ldv;
+    int nv;             // leading ext columns taken from V itself (Gram block S = V'V); 0 or NBP
+    const double* A;    // window row 0, first trailing column
+    int64_t lda;
+    int64_t rows;       // valid rows of A in the window
+    int na;             // trailing columns
+    int nchunks;        // ceil(rows / KC)
+    int a_aligned;      // 1: every A column start is 16B aligned (bulk copies legal)
+    double* Wp;         // partials: [split][next_pad][NBP]
+    int64_t pstride;    // elements between consecutive partials
+};
+
+template <int NBP, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs a) {
+    constexpr int NCW = WM * WN;
+    constexpr int WTM = NBP / WM, WTN = BN / WN;
+    constexpr int MI = WTM / 8, NJ = WTN / 8;
+    static_assert(WTM % 8 == 0 && WTN % 8 == 0, "warp tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][NBP][LDK]
+    double* sB = sV + STAGES * NBP * LDK;                // [STAGES][BN][LDK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BN * LDK);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int next = a.nv + a.na;
+    const int col0 = blockIdx.x * BN;
+    const int ncols_tile = min(BN, next - col0);
+    const int cps = (a.nchunks + gridDim.y - 1) / gridDim.y;
+    const int ch0 = blockIdx.y * cps;
+    const int nit = max(min(ch0 + cps, a.nchunks) - ch0, 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ===== TMA producer warp =====
+        for (int it = 0; it < nit; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            const int64_t krow = (int64_t)(ch0 + it) * KC;
+            const int64_t left = a.rows - krow;
+            const int nvalid = left >= KC ? KC : (int)left;          // valid A rows in this chunk (>= 1)
+            const int nbulk = a.a_aligned ? (nvalid & ~1) : 0;        // rows moved by TMA per A column
+            double* dV = sV + (size_t)s * NBP * LDK;
+            double* dB = sB + (size_t)s * BN * LDK;
+            // generic-proxy fill of what TMA cannot move (ragged tail / unaligned user storage)
+            uint32_t bytes = NBP * KC * 8;
+            for (int c = lane; c < ncols_tile; c += 32) {
+                const int jg = col0 + c;
+                if (jg >= a.nv && nbulk < KC) {
+                    const double* src = a.A + (int64_t)(jg - a.nv) * a.lda + krow;
+                    double* dst = dB + c * LDK;
+                    for (int r = nbulk; r < KC; ++r) dst[r] = r < nvalid ? src[r] : 0.0;
+                }
+            }
+            // every lane needs the byte total: count columns of each kind in this tile
+            {
+                const int nvcols = max(min(a.nv - col0, ncols_tile), 0);
+                bytes += (uint32_t)nvcols * KC * 8 + (uint32_t)(ncols_tile - nvcols) * nbulk * 8;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
+            __syncwarp();
+            for (int c = lane; c < NBP; c += 32) bulk_g2s(dV + c * LDK, a.V + (int64_t)c * a.ldv + krow, KC * 8, &full[s]);
+            for (int c = lane; c < ncols_tile; c += 32) {
+                const int jg = col0 + c;
+                if (jg < a.nv) {
+                    bulk_g2s(dB + c * LDK, a.V + (int64_t)jg * a.ldv + krow, KC * 8, &full[s]);
+                } else if (nbulk > 0) {
+                    bulk_g2s(dB + c * LDK, a.A + (int64_t)(jg - a.nv) * a.lda + krow, nbulk * 8, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== DMMA consumer warps =====
+    const int wm = warp / WN, wn = warp % WN;
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int frag = (lane >> 2) * LDK + (lane & 3);
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const double* v = sV + (size_t)s * NBP * LDK + wm * WTM * LDK + frag;
+        const double* b = sB + (size_t)s * BN * LDK + wn * WTN * LDK + frag;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            double af[MI], bf[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) af[i] = v[i * 8 * LDK + kk * 4];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bf[j] = b[j * 8 * LDK + kk * 4];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    double* out = a.Wp + (int64_t)blockIdx.y * a.pstride;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int row = wm * WTM + i * 8 + (lane >> 2);
+            const int col = col0 + wn * WTN + j * 8 + (lane & 3) * 2;
+            if (col < next) out[(int64_t)col * NBP + row] = acc[i][j][0];
+            if (col + 1 < next) out[(int64_t)(col + 1) * NBP + row] = acc[i][j][1];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_cvy:  C(rows x ncols) += V(rows x nbp) * Y(nbp x ncols)   on rows >= row_lo   ("NN", K = nbp)
+//   Y already carries the minus sign and T' (ymake), so this is A_trail <- (I - V T' V') A_trail.
+//   grid: (row tiles of BM, column tiles of BN); 2 CTAs per SM so one CTA's C-tile load/store
+//   overlaps the other's MMA main loop.  CTA: WM*WN consumer warps (64x32 warp tiles) + 1 TMA warp.
+//   V and Y live in handle-owned, padded, 16B-aligned buffers -> every stage is pure TMA.
+// ------------------------------------------------------------------------------------------------
+struct GemmCvyArgs {
+    double* C;          // window row 0, first column
+    int64_t ldc;
+    int64_t rows;       // valid rows in the window
+    int64_t row_lo;     // rows below this index (window-relative) are left untouched
+    int ncols;
+    const double* V;    // window row 0; ldv multiple of BM, rows padded with zeros
+    int64_t ldv;
+    const double* Y;    // nbp x ncols_pad, ld = ldy
+    int64_t ldy;
+    int nbp;            // multiple of KC
+};
+
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+__global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
+    constexpr int NCW = WM * WN;
+    constexpr int WTM = BM / WM, WTN = BN / WN;
+    constexpr int MI = WTM / 8, NJ = WTN / 8;
+    constexpr int LDV = BM + 4;   // (BM + 4) % 16 == 4 -> conflict-free A-fragment loads
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][KC][LDV]
+    double* sY = sV + STAGES * KC * LDV;                 // [STAGES][BN][LDK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sY + STAGES * BN * LDK);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int nit = a.nbp / KC;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ===== TMA producer warp =====
+        for (int it = 0; it < nit; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(KC * BM * 8 + BN * KC * 8));
+            __syncwarp();
+            double* dV = sV + (size_t)s * KC * LDV;
+            double* dY = sY + (size_t)s * BN * LDK;
+            const int k0 = it * KC;
+            for (int c = lane; c < KC; c += 32) bulk_g2s(dV + c * LDV, a.V + (int64_t)(k0 + c) * a.ldv + m0, BM * 8, &full[s]);
+            for (int c = lane; c < BN; c += 32) bulk_g2s(dY + c * LDK, a.Y + (int64_t)(n0 + c) * a.ldy + k0, KC * 8, &full[s]);
+        }
+        return;
+    }
+
+    // ===== DMMA consumer warps =====
+    const int wm = warp / WN, wn = warp % WN;
+    const int64_t rbase = m0 + wm * WTM + (lane >> 2);
+    const int cbase = n0 + wn * WTN + (lane & 3) * 2;
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t row = rbase + i * 8;
+        const bool rok = row >= a.row_lo && row < a.rows;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int col = cbase + j * 8;
+            const double* p = a.C + (int64_t)col * a.ldc + row;
+            acc[i][j][0] = (rok && col < a.ncols) ? *p : 0.0;
+            acc[i][j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
+        }
+    }
+    const int fragA = (lane & 3) * LDV + (lane >> 2);
+    const int fragB = (lane >> 2) * LDK + (lane & 3);
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const double* v = sV + (size_t)s * KC * LDV + wm * WTM + fragA;
+        const double* y = sY + (size_t)s * BN * LDK + wn * WTN * LDK + fragB;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            double af[MI], bf[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LDV + i * 8];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bf[j] = y[j * 8 * LDK + kk * 4];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t row = rbase + i * 8;
+        const bool rok = row >= a.row_lo && row < a.rows;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int col = cbase + j * 8;
+            double* p = a.C + (int64_t)col * a.ldc + row;
+            if (rok && col < a.ncols) *p = acc[i][j][0];
+            if (rok && col + 1 < a.ncols) *(p + a.ldc) = acc[i][j][1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tinv:  Linv = (I + stril(S))^{-1},  S = sum of the Gram partials (first NBP ext columns of Wp).
+//   With |v|^2 = 2 the compact-WY factor obeys T^{-1} = I + striu(V'V), so Linv == T'.
+//   One CTA; 32x32 diagonal blocks by forward substitution, then two levels of
+//   X21 = -X22 (L21 X11).
+// ------------------------------------------------------------------------------------------------
+template <int NBP>
+__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Wp, int64_t pstride, int nsplit,
+                                                 double* __restrict__ Linv) {
+    constexpr int LDL = NBP + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
+    double* T = L + NBP * LDL;                          // scratch, 4 * 32 * 33 doubles
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
+        const int i = e % NBP, j = e / NBP;
+        double s = 0.0;
+        if (i > j)
+            for (int p = 0; p < nsplit; ++p) s += Wp[(int64_t)p * pstride + (int64_t)j * NBP + i];
+        L[j * LDL + i] = s;
+    }
+    __syncthreads();
+    // diagonal 32x32 blocks: X = (I + N)^{-1}; thread = one column of one block
+    constexpr int ND = NBP / 32;
+    if (tid < ND * 32) {
+        const int d = tid >> 5, j = tid & 31;
+        const double* Ld = L + (d * 32) * LDL + d * 32;
+        double* X = T + d * 32 * 33;   // (i,j) at j*33 + i
+        for (int i = 0; i < 32; ++i) X[j * 33 + i] = (i == j) ? 1.0 : 0.0;
+        for (int i = 1; i < 32; ++i) {
+            double accv = 0.0;
+            for (int k = 0; k < i; ++k) accv += Ld[k * LDL + i] * X[j * 33 + k];
+            if (i > j) X[j * 33 + i] = -accv;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < ND * 32 * 32; e += blockDim.x) {
+        const int d = e / 1024, r = e % 1024, i = r % 32, j = r / 32;
+        L[(d * 32 + j) * LDL + d * 32 + i] = T[d * 32 * 33 + j * 33 + i];
+    }
+    __syncthreads();
+    // merge levels
+    for (int bs = 32; bs < NBP; bs *= 2) {
+        const int npairs = NBP / (2 * bs);
+        for (int p = 0; p < npairs; ++p) {
+            const int o = p * 2 * bs;
+            // T = L21 * X11      (bs x bs), T(i,j) at j*bs + i   (bs*bs <= 4096 <= scratch)
+            for (int e = tid; e < bs * bs; e += blockDim.x) {
+                const int i = e % bs, j = e / bs;
+                double s = 0.0;
+                for (int k = j; k < bs; ++k) s += L[(o + k) * LDL + o + bs + i] * L[(o + j) * LDL + o + k];
+                T[j * bs + i] = s;
+            }
+            __syncthreads();
+            // X21 = -X22 * T
+            for (int e = tid; e < bs * bs; e += blockDim.x) {
+                const int i = e % bs, j = e / bs;
+                double s = 0.0;
+                for (int k = 0; k <= i; ++k) s += L[(o + bs + k) * LDL + o + bs + i] * T[j * bs + k];
+                L[(o + j) * LDL + o + bs + i] = -s;
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
+        const int i = e % NBP, j = e / NBP;
+        Linv[e] = (i >= j) ? L[j * LDL + i] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ymake:  Y(NBP x na) = -Linv * (sum of W partials)     (W = ext columns [nv, nv+na))
+//   CTA = YCOLS columns; thread = (row i, half of the columns).
+// ------------------------------------------------------------------------------------------------
+constexpr int YCOLS = 32;
+template <int NBP>
+__global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Wp, int64_t pstride, int nsplit, int nv,
+                                                  int na, const double* __restrict__ Linv, double* __restrict__ Y,
+                                                  int64_t ldy) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sL = reinterpret_cast<double*>(smem_raw);   // [NBP][NBP] col-major
+    double* sW = sL + NBP * NBP;                         // [YCOLS][NBP]
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * YCOLS;
+    const int nc = min(YCOLS, na - c0);
+    for (int e = tid; e < NBP * NBP; e += blockDim.x) sL[e] = Linv[e];
+    for (int e = tid; e < YCOLS * NBP; e += blockDim.x) {
+        const int k = e % NBP, j = e / NBP;
+        double s = 0.0;
+        if (j < nc)
+            for (int p = 0; p < nsplit; ++p) s += Wp[(int64_t)p * pstride + (int64_t)(nv + c0 + j) * NBP + k];
+        sW[e] = s;
+    }
+    __syncthreads();
+    constexpr int TPR = 256 / NBP;           // threads per row (2 for 128, 8 for 32)
+    constexpr int CPT = YCOLS / TPR;         // columns per thread
+    const int i = tid % NBP, jh = tid / NBP;
+    double acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.0;
+    for (int k = 0; k < NBP; ++k) {
+        const double l = sL[k * NBP + i];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[j] += l * sW[(jh * CPT + j) * NBP + k];
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int col = c0 + jh * CPT + j;
+        if (col < na) Y[(int64_t)col * ldy + i] = -acc[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel:  cooperative, persistent factorisation of an mp x ncols (ncols <= IB) panel.
+//   Each CTA keeps a slab of rows in shared memory for the whole kernel.  One grid-wide
+//   reduction per column: the same pass that applies reflector j also accumulates
+//   x'a_c (x = next pivot column, rows > j) for every remaining column c, so that after the barrier
+//   every CTA can form   s=|x|, alpha, f   and   w_c = v'a_c = f (x'a_c - alpha a_c[j])   locally
+//   (S:129-131 and S:208 in one reduction).  Partials are summed in CTA order (deterministic).
+//   Also writes the packed V block (zero above the diagonal, zero padding rows) for the GEMMs.
+// ------------------------------------------------------------------------------------------------
+struct PanelArgs {
+    double* P;            // panel top-left (row = pivot row of column 0)
+    int64_t ldp;
+    int64_t mp;           // rows
+    int ncols;            // active columns (<= IB)
+    double* alpha;        // alpha[0:ncols]
+    double* Vout;         // V block column 0 of this sub-panel, window row 0 (may be null)
+    int64_t ldv;
+    int64_t vtop;         // window rows above the panel top (zero-filled in Vout)
+    int64_t vrows;        // total window rows incl. padding (zero-filled below vtop+mp)
+    int rows_per_cta;
+    int lds;              // slab leading dimension (>= rows_per_cta, odd)
+    double* part;         // [2][gridDim.x][IB]
+    double* piv;          // [2][IB]
+    unsigned long long* bar;
+    unsigned long long bar_base;   // barrier counter value at launch
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ULL);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* S = reinterpret_cast<double*>(smem_raw);   // [IB][lds]
+    __shared__ double red[PANEL_THREADS / 32][IB];
+    __shared__ double tot[IB];
+    __shared__ double pv[IB];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = PANEL_THREADS / 32;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int64_t row0 = (int64_t)cta * a.rows_per_cta;
+    const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - row0));
+    const int lds = a.lds, nc = a.ncols;
+
+    // load slab (coalesced along rows)
+    for (int c = warp; c < nc; c += NW)
+        for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
+    __syncthreads();
+
+    // partial dots of column 0 against every column (all rows), and the pivot row
+    for (int c = warp; c < nc; c += NW) {
+        double acc = 0.0;
+        for (int r = lane; r < nr; r += 32) acc += S[r] * S[c * lds + r];
+        acc = warp_sum(acc);
+        if (lane == 0) a.part[((size_t)0 * G + cta) * IB + c] = acc;
+    }
+    if (cta == 0 && tid < nc) a.piv[tid] = S[tid * lds + 0];
+
+    unsigned long long target = a.bar_base;
+    for (int j = 0; j < nc; ++j) {
+        target += G;
+        grid_barrier(a.bar, target);
+        const int buf = j & 1;
+        // deterministic reduction of the partials: thread (q = warp, c = lane) sums CTAs q, q+NW, ...
+        {
+            double acc = 0.0;
+            if (lane >= j && lane < nc)
+                for (int g = warp; g < G; g += NW) acc += __ldcg(&a.part[((size_t)buf * G + g) * IB + lane]);
+            red[warp][lane] = acc;
+        }
+        __syncthreads();
+        if (tid < IB) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) s += red[q][tid];
+            tot[tid] = s;
+            pv[tid] = (tid >= j && tid < nc) ? __ldcg(&a.piv[buf * IB + tid]) : 0.0;
+        }
+        __syncthreads();
+        // S:129-131
+        const double xj = pv[j];
+        const double s = sqrt(tot[j]);
+        const double sg = xj > 0.0 ? 1.0 : (xj < 0.0 ? -1.0 : 0.0);   // sign(0) == 0 as in S:8
+        const double alpha = -sg * s;
+        const double f = 1.0 / sqrt(s * (s + fabs(xj)));
+        if (cta == 0 && tid == 0) a.alpha[j] = alpha;
+        // local index of pivot row j inside this slab (rows before it are finished R entries)
+        const int64_t rj = (int64_t)j - row0;
+        const int r_lo = rj < 0 ? 0 : (rj > nr ? nr : (int)rj);   // first active local row
+        // step 1: v = f (x - alpha e_j) in place; next pivot column updated in place
+        const bool has_next = j + 1 < nc;
+        const double w1 = has_next ? f * (tot[j + 1] - alpha * pv[j + 1]) : 0.0;
+        for (int r = r_lo + tid; r < nr; r += PANEL_THREADS) {
+            double x = S[j * lds + r];
+            if (row0 + r == j) x -= alpha;
+            const double v = f * x;
+            S[j * lds + r] = v;
+            if (has_next) S[(j + 1) * lds + r] -= v * w1;
+        }
+        __syncthreads();
+        if (has_next) {
+            const int nbuf = buf ^ 1;
+            // rows that enter the next column's dots: global row >= j+1
+            const int64_t rj1 = (int64_t)j + 1 - row0;
+            const int r_lo1 = rj1 < 0 ? 0 : (rj1 > nr ? nr : (int)rj1);
+            // step 2: tasks t = j+1 .. nc-1; t == j+1 is the self-dot, others update + dot
+            for (int c = j + 1 + warp; c < nc; c += NW) {
+                double acc = 0.0;
+                if (c == j + 1) {
+                    for (int r = r_lo1 + lane; r < nr; r += 32) {
+                        const double x = S[c * lds + r];
+                        acc += x * x;
+                    }
+                } else {
+                    const double wc = f * (tot[c] - alpha * pv[c]);
+                    for (int r = r_lo + lane; r < nr; r += 32) {
+                        const double t = S[c * lds + r] - S[j * lds + r] * wc;
+                        S[c * lds + r] = t;
+                        if (r >= r_lo1) acc += S[(j + 1) * lds + r] * t;
+                    }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) a.part[((size_t)nbuf * G + cta) * IB + c] = acc;
+            }
+            if (cta == 0) {
+                __syncthreads();
+                if (tid > j && tid < nc) a.piv[nbuf * IB + tid] = S[tid * lds + (j + 1)];
+            }
+        }
+    }
+    __syncthreads();
+    // write back the factored slab, and the packed V block
+    for (int c = warp; c < nc; c += NW)
+        for (int r = lane; r < nr; r += 32) a.P[(int64_t)c * a.ldp + row0 + r] = S[c * lds + r];
+    if (a.Vout) {
+        for (int c = warp; c < IB; c += NW) {
+            double* vc = a.Vout + (int64_t)c * a.ldv;
+            for (int r = lane; r < nr; r += 32) vc[a.vtop + row0 + r] = (c < nc && row0 + r >= c) ? S[c * lds + r] : 0.0;
+            if (cta == 0)
+                for (int64_t r = lane; r < a.vtop; r += 32) vc[r] = 0.0;
+            if (cta == G - 1)
+                for (int64_t r = a.vtop + a.mp + lane; r < a.vrows; r += 32) vc[r] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_v: copy the Householder block stored in place in A (lower trapezoid incl. diagonal) into the
+// packed V buffer for the solve phase (S:232-242 reads H in place; the GEMM path wants zeros above).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_v(const double* __restrict__ A, int64_t lda, int64_t mp, int kb, double* __restrict__ V,
+                         int64_t ldv, int64_t vtop, int64_t vrows, int nbp) {
+    const int c = blockIdx.y;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < vrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pr = r - vtop;   // panel-relative row
+        double v = 0.0;
+        if (c < kb && pr >= c && pr < mp) v = A[(int64_t)c * lda + pr];
+        V[(int64_t)c * ldv + r] = v;
+    }
+    (void)nbp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// back-substitution step (S:256-282), column oriented: solve the bs x bs diagonal block
+//   x_blk = R_bb^{-1} y_blk   (R_bb = triu(A_bb,1) + diag(alpha))   in every CTA (one warp),
+// then y[0:c0) -= R[0:c0, blk] x_blk on the CTA's slice of rows.  CTA 0 publishes x_blk.
+// ------------------------------------------------------------------------------------------------
+constexpr int BS_BLK = 32;
+__global__ void __launch_bounds__(256) k_backsolve_step(const double* __restrict__ Ablk, int64_t lda,
+                                                        const double* __restrict__ alpha, double* __restrict__ y,
+                                                        int64_t ldy, int nrhs, double* __restrict__ x, int64_t ldx,
+                                                        int64_t c0, int bs) {
+    // Ablk: pointer to (row 0, first column of the block) in local storage; c0 = global index of that column
+    __shared__ double sx[BS_BLK];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int rhs = 0; rhs < nrhs; ++rhs) {
+        double* yr = y + (int64_t)rhs * ldy;
+        if (tid < 32) {
+            double yk = lane < bs ? yr[c0 + lane] : 0.0;
+            for (int i = bs - 1; i >= 0; --i) {
+                const double xi = __shfl_sync(0xffffffffu, yk, i) / alpha[c0 + i];
+                if (lane == i) yk = xi;
+                if (lane < i) yk -= Ablk[(int64_t)i * lda + c0 + lane] * xi;
+            }
+            sx[lane] = yk;
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && tid < bs) x[(int64_t)rhs * ldx + c0 + tid] = sx[tid];
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < c0; r += (int64_t)gridDim.x * blockDim.x) {
+            double acc = 0.0;
+            for (int k = 0; k < bs; ++k) acc += Ablk[(int64_t)k * lda + r] * sx[k];
+            yr[r] -= acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unblocked path (nb = 1, BASELINE config 2): one reflector per step.
+//   k_house1: S:129-135 for column j (one CTA): norm via warp-shuffle tree, scale in place, and a
+//             16B-aligned copy of v (zero-padded to a multiple of 2) for TMA staging.
+//   k_apply1: S:198-213: each CTA owns CW trailing columns; v and the column tile are staged into
+//             shared memory with TMA bulk copies, one warp-shuffle dot + axpy per column, written
+//             back once (one read + one write of the trailing matrix per step).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) k_house1(double* __restrict__ col, int64_t len, double* __restrict__ alpha,
+                                                    double* __restrict__ vout) {
+    __shared__ double red[32];
+    __shared__ double sc[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double acc = 0.0;
+    for (int64_t i = tid; i < len; i += 1024) {
+        const double x = col[i];
+        acc += x * x;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double t = red[lane];
+        t = warp_sum(t);
+        if (lane == 0) {
+            const double x0 = col[0];
+            const double s = sqrt(t);
+            const double sg = x0 > 0.0 ? 1.0 : (x0 < 0.0 ? -1.0 : 0.0);
+            const double al = -sg * s;
+            *alpha = al;
+            sc[0] = al;
+            sc[1] = 1.0 / sqrt(s * (s + fabs(x0)));
+        }
+    }
+    __syncthreads();
+    const double al = sc[0], f = sc[1];
+    for (int64_t i = tid; i < len; i += 1024) {
+        double x = col[i];
+        if (i == 0) x -= al;
+        x *= f;
+        col[i] = x;
+        vout[i] = x;
+    }
+    if (tid == 0) vout[len] = 0.0;   // pad so the staged copy is a whole number of 16B units
+}
+
+constexpr int A1_CW = 2;         // columns per CTA
+constexpr int A1_THREADS = 256;
+// staged variant: requires (len_pad * 8 * (A1_CW + 1)) bytes of smem, 16B-aligned column starts
+__global__ void __launch_bounds__(A1_THREADS) k_apply1_tma(const double* __restrict__ v, int64_t len,
+                                                          double* __restrict__ C, int64_t ldc, int ncols, int aligned) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ double red[A1_CW][A1_THREADS / 32];
+    const int64_t lenp = (len + 1) & ~(int64_t)1;
+    double* sv = reinterpret_cast<double*>(smem_raw);
+    double* sc = sv + lenp;   // [A1_CW][lenp]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * A1_CW;
+    const int nc = min(A1_CW, ncols - c0);
+    const int64_t nb = aligned ? (len & ~(int64_t)1) : 0;   // elements per column moved by TMA
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // generic fill of what TMA cannot move
+    for (int c = 0; c < nc; ++c)
+        for (int64_t i = nb + tid; i < len; i += A1_THREADS) sc[c * lenp + i] = C[(int64_t)(c0 + c) * ldc + i];
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = (uint32_t)(lenp * 8) + (uint32_t)(nc * nb * 8);
+        mbar_arrive_expect_tx(&bar, bytes);
+        // chunked: a single bulk copy is limited in size; 32 KB pieces
+        for (int64_t o = 0; o < lenp; o += 4096) bulk_g2s(sv + o, v + o, (uint32_t)(min((int64_t)4096, lenp - o) * 8), &bar);
+        for (int c = 0; c < nc; ++c)
+            for (int64_t o = 0; o < nb; o += 4096)
+                bulk_g2s(sc + c * lenp + o, C + (int64_t)(c0 + c) * ldc + o, (uint32_t)(min((int64_t)4096, nb - o) * 8), &bar);
+    }
+    mbar_wait(&bar, 0);
+    for (int c = 0; c < nc; ++c) {
+        double acc = 0.0;
+        for (int64_t i = tid; i < len; i += A1_THREADS) acc += sv[i] * sc[c * lenp + i];   // S:208 partialdot
+        acc = warp_sum(acc);
+        if (lane == 0) red[c][warp] = acc;
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < A1_THREADS / 32; ++w) s += red[c][w];
+        double* out = C + (int64_t)(c0 + c) * ldc;
+        for (int64_t i = tid; i < len; i += A1_THREADS) out[i] = sc[c * lenp + i] - sv[i] * s;   // S:209 hotloop!
+    }
+}
+// direct variant (column tile does not fit in shared memory): two passes, second read hits L2
+__global__ void __launch_bounds__(A1_THREADS) k_apply1_direct(const double* __restrict__ v, int64_t len,
+                                                             double* __restrict__ C, int64_t ldc, int ncols) {
+    __shared__ double red[A1_THREADS / 32];
+    __shared__ double sdot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
+        double* col = C + (int64_t)c * ldc;
+        double acc = 0.0;
+        for (int64_t i = tid; i < len; i += A1_THREADS) acc += v[i] * col[i];
+        acc = warp_sum(acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < A1_THREADS / 32; ++w) s += red[w];
+            sdot = s;
+        }
+        __syncthreads();
+        const double s = sdot;
+        for (int64_t i = tid; i < len; i += A1_THREADS) col[i] -= v[i] * s;
+        __syncthreads();
+    }
+}
+
+// partialdot (S:42-49) as a standalone primitive: one CTA, warp-shuffle tree.
+__global__ void __launch_bounds__(1024, 1) k_partialdot(const double* __restrict__ x, const double* __restrict__ y,
+                                                        int64_t i0, int64_t i1, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double acc = 0.0;
+    for (int64_t i = i0 + tid; i < i1; i += 1024) acc += x[i] * y[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double t = red[lane];
+        t = warp_sum(t);
+        if (lane == 0) *out = t;
+    }
+}
+
+// counter-based U[0,1) fill, bit-identical to oracle/dhqr_oracle.c:dhqr_oracle_uniform
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void k_fill_uniform(uint64_t seed, int64_t i0, int64_t j0, int64_t m, int64_t n, double* __restrict__ A,
+                               int64_t lda) {
+    const uint64_t sh = mix64(seed);
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+            const uint64_t z = mix64(sh ^ ((uint64_t)(j0 + j) * 0xD1342543DE82EF95ULL + (uint64_t)(i0 + i)));
+            A[j * lda + i] = (double)(z >> 11) * 0x1.0p-53;
+        }
+}
+
+}  // namespace dhqr

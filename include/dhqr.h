@@ -1,0 +1,123 @@
+/*
+ * dhqr.h — C-ABI of libdhqr.so: B200-native (sm_100a) blocked Householder QR behind
+ * DistributedHouseholderQR.jl's qr! / \ entry points.
+ *
+ * The reference (pure Julia) has no FFI of its own; each entry point below names the Julia
+ * method it replaces (S:n = src/DistributedHouseholderQR.jl:n of the reference).  A Julia shim
+ * (distributedhouseholderqr.jl_b200/julia/DistributedHouseholderQRB200.jl)
+ * ccall's these with CuPtr{Float64}; the Python host package binds them with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / CUDA.jl types in any signature.
+ *   - every function returns int: 0 = ok; < 0 = -(1-based index of the offending argument),
+ *     LAPACK-info style; > 0 = CUDA/NCCL failure (text via dhqr_last_error()).
+ *   - matrices are column-major double with leading dimension lda >= m (Julia Matrix /
+ *     localpart(DArray)).  Device pointers unless the name says _host_.
+ *   - stream-ordered: work is enqueued on the caller's cudaStream_t (passed as void*; NULL =
+ *     legacy default stream) and the call returns without synchronising, except the _host_
+ *     entry points, which block until their result is in host memory.
+ *   - no pointer to caller memory is retained after return; workspace lives in the handle.
+ *   - SPMD for multi-GPU: every rank (one process per GPU) makes the same call with its own
+ *     column block (col0 = first global column, 0-based = the reference's LocalColumnBlock.dj, S:34).
+ *   - storage format on return == the reference's (S:127-135): Householder vectors scaled to
+ *     |v|^2 = 2 in the lower trapezoid INCLUDING the diagonal, R's strict upper triangle above
+ *     it, diag(R) in alpha.
+ */
+#ifndef DHQR_H
+#define DHQR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dhqr_context *dhqr_handle;
+
+#define DHQR_VERSION 100 /* 0.1.0 */
+#define DHQR_NCCL_UNIQUE_ID_BYTES 128
+
+/* ---- library / handle -------------------------------------------------------------------- */
+int dhqr_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *dhqr_last_error(void);
+
+/* Single-GPU handle on CUDA device `device` (replaces nothing in the reference: the Julia
+ * package keeps no state; the handle owns workspace and the grid-barrier words). */
+int dhqr_create(dhqr_handle *h, int device);
+/* Multi-GPU handle: rank `rank` of `nranks`, NCCL communicator built from `unique_id`
+ * (DHQR_NCCL_UNIQUE_ID_BYTES bytes from dhqr_nccl_unique_id() on rank 0, shipped by the host:
+ * torch.distributed in Python, Distributed.jl in Julia).  Replaces the reference's use of
+ * Distributed/SharedArrays (S:116-118, S:141-143, S:227-229, S:260-267, S:302, S:318). */
+int dhqr_create_dist(dhqr_handle *h, int device, const void *unique_id, int rank, int nranks);
+int dhqr_nccl_unique_id(void *out_unique_id);
+int dhqr_destroy(dhqr_handle h);
+/* Tunables: "nb" (outer panel width, multiple of 32 in [32,128], default 128), "panel_ctas"
+ * (CTAs of the cooperative panel kernel, 0 = one per SM), "sync" (1 = cudaStreamSynchronize and
+ * error-check after every entry point; debugging). */
+int dhqr_set_option(dhqr_handle h, const char *key, int64_t value);
+int dhqr_get_option(dhqr_handle h, const char *key, int64_t *value);
+/* Number of kernel launches enqueued by this handle since creation (bench.py: gpu_launches). */
+int dhqr_launch_count(dhqr_handle h, int64_t *count);
+
+/* ---- qr!  (S:311-315 -> householder! S:113-120 -> _householder! S:122-148 -> _householder_inner!
+ *            S:198-213 with partialdot S:42-49 and hotloop! S:156-160) --------------------------
+ * Factor the m x n_global matrix whose columns [col0, col0+n_local) are stored in dA_local
+ * (m x n_local, lda).  In place.  d_alpha (length n_global) receives diag(R) on every rank.
+ * nb: 0 = handle default (blocked, compact-WY trailing update on the fp64 tensor pipe);
+ *     1 = unblocked column-by-column path (BASELINE config 2);
+ *     otherwise a multiple of 32 in [32,128]. */
+int dhqr_qr_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                double *dA_local, int64_t lda, double *d_alpha, int nb, void *stream);
+
+/* ---- \  (S:317-321 -> solve_householder! S:284-294) ---------------------------------------- */
+/* b <- Q'b  (_solve_householder1! S:226-242 / S:215-224).  d_b: m x nrhs, ldb >= m, in place;
+ * identical on every rank on entry and on return. */
+int dhqr_apply_qt_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                      const double *dA_local, int64_t lda, double *d_b, int64_t ldb, int nrhs,
+                      void *stream);
+/* b[0:n] <- R^{-1} b[0:n]  (_solve_householder2! S:256-282 / S:244-254), R = triu(A,1)+diag(alpha). */
+int dhqr_backsolve_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                       const double *dA_local, int64_t lda, const double *d_alpha, double *d_b,
+                       int64_t ldb, int nrhs, void *stream);
+/* Both phases (solve_householder! S:284-294): x = d_b[0:n_global, :] on return. */
+int dhqr_solve_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                   const double *dA_local, int64_t lda, const double *d_alpha, double *d_b,
+                   int64_t ldb, int nrhs, void *stream);
+
+/* ---- host-buffer entry points (single GPU): the call a CPU-side user of qr! / \ makes -------
+ * hA (m x n, lda) is copied to the device, factored, and copied back with alpha; blocks until
+ * the result is in host memory.  Pinned host memory makes the copies asynchronous to each other. */
+int dhqr_qr_host_f64(dhqr_handle h, int64_t m, int64_t n, double *hA, int64_t lda, double *h_alpha,
+                     int nb);
+/* x = H \ b from a host-resident factorisation (hA, h_alpha) and host b (length m); x length n. */
+int dhqr_ldiv_host_f64(dhqr_handle h, int64_t m, int64_t n, const double *hA, int64_t lda,
+                       const double *h_alpha, const double *h_b, double *h_x);
+
+/* ---- primitives exposed for parity tests ---------------------------------------------------- */
+/* partialdot(a, b, is, ::Type{<:Real}) (S:42-49): *d_out = sum_{i in [i0,i1)} a[i]*b[i] (0-based). */
+int dhqr_partialdot_f64(dhqr_handle h, const double *d_a, const double *d_b, int64_t i0, int64_t i1,
+                        double *d_out, void *stream);
+/* A[i,j] = U[0,1) from the counter-based generator keyed on (seed, i0+i, j0+j); bit-identical to
+ * oracle/dhqr_oracle.c:dhqr_oracle_uniform (mirrors rand(T,m,n) at test/runtests.jl:45-46). */
+int dhqr_fill_uniform_f64(dhqr_handle h, uint64_t seed, int64_t i0, int64_t j0, int64_t m, int64_t n,
+                          double *dA, int64_t lda, void *stream);
+
+/* ---- kernel-level hooks (unit tests of the individual CUDA kernels; not part of the drop-in) --
+ * gemm_vta : Wext[nbp x (nbp+ncols)] = V' * [V | C]  (split over rows, partials reduced by ymake/tinv)
+ * tinv     : Linv = (I + stril(V'V))^{-1}
+ * ymake    : Y = -Linv * W
+ * gemm_cvy : C += V * Y   on rows >= row_lo
+ * All operate on the handle's internal V buffer, filled from (dV, ldv) by the call. */
+int dhqr_k_block_reflector_f64(dhqr_handle h, int64_t rows, int nbp, const double *dV, int64_t ldv,
+                               int64_t row_lo, int ncols, double *dC, int64_t ldc, double *d_linv_out,
+                               void *stream);
+/* Panel kernel: factor the rows x ncols (ncols <= 32) panel at dP in place (reference recurrences
+ * S:127-135 + S:208-209 restricted to the panel), alpha -> d_alpha[0:ncols]. */
+int dhqr_k_panel_f64(dhqr_handle h, int64_t rows, int ncols, double *dP, int64_t ldp, double *d_alpha,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHQR_H */

@@ -1,0 +1,263 @@
+/*
+ * dhqr_oracle.c — CPU restatement of DistributedHouseholderQR.jl's hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may call into this file.  The product
+ * (libdhqr.so) never links, loads or falls back to anything in oracle/.
+ *
+ * Every function cites the reference lines it follows, with
+ *   S:n = /root/reference/src/DistributedHouseholderQR.jl line n.
+ *
+ * Parity status: the reference ships no golden vectors (its tests draw from Julia's
+ * Xoshiro stream, test/runtests.jl:6,45-46) and Julia is not installed, so this
+ * restatement is pinned by (i) the reference's own test properties (normal-equation
+ * residual < 8x LAPACK's, test/runtests.jl:51,62,81; partialdot ~ dot on suffixes,
+ * test/partialdot.jl:15-19), (ii) LAPACK dgeqrf through the storage-format identity
+ * alpha = diag(R), triu(H,1) = triu(R,1), H[j,j]^2 = tau_j, and
+ * (iii) committed fixtures under tests/golden/.  Bitwise parity with the Julia binary
+ * is UNPINNED (no Julia here); see DESIGN.md "Oracle".
+ *
+ * Layout: column-major doubles, leading dimension lda >= m (Julia Matrix / localpart(DArray)).
+ * A "column block" is the localpart of the reference's DArray with a (1,P) process grid
+ * (test/runtests.jl:71): all m rows of a contiguous global column range (S:33).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define DHQR_ORACLE_VERSION 1
+
+int dhqr_oracle_version(void) { return DHQR_ORACLE_VERSION; }
+
+int dhqr_oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* S:8  alphafactor(x::Real) = -sign(x)   (sign(0) == 0, mirrored on purpose) */
+double dhqr_oracle_alphafactor(double x) { return x > 0.0 ? -1.0 : (x < 0.0 ? 1.0 : -0.0 * 0.0); }
+
+/* S:42-49  partialdot(a, b, is, ::Type{<:Real}): sum_{i in is} a[i]*b[i].
+ * The reference marks the loop @simd (free re-association); four independent partial
+ * sums stand in for the SIMD lanes.  i0..i1 are 0-based, i1 exclusive. */
+double dhqr_oracle_partialdot(const double *a, const double *b, int64_t i0, int64_t i1) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t i = i0;
+    for (; i + 4 <= i1; i += 4) {
+        s0 += a[i] * b[i];
+        s1 += a[i + 1] * b[i + 1];
+        s2 += a[i + 2] * b[i + 2];
+        s3 += a[i + 3] * b[i + 3];
+    }
+    for (; i < i1; ++i) s0 += a[i] * b[i];
+    return (s0 + s1) + (s2 + s3);
+}
+
+/* S:156-160  hotloop!(Hl, Hj, s, is, jj, ::Type{<:Real}): Hl[i,jj] -= Hj[i]*s */
+static void hotloop(double *col, const double *hj, double s, int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; ++i) col[i] -= hj[i] * s;
+}
+
+/* S:129  norm(view(Hl, j:m, j)) -> LinearAlgebra.norm -> OpenBLAS dnrm2 (OpenBLAS_jll
+ * 0.3.23+4, Manifest.toml:139-142; not vendored).  x86-64 OpenBLAS accumulates the squares
+ * in extended precision; long double does the same here.  Any faithful 2-norm is within the
+ * stated tolerances (parity unpinned at this call boundary). */
+static double nrm2(const double *x, int64_t n) {
+    long double s = 0.0L;
+    for (int64_t i = 0; i < n; ++i) s += (long double)x[i] * (long double)x[i];
+    return (double)sqrtl(s);
+}
+
+/* A column block: LocalColumnBlock{Al, dj, colrange} of S:26-40.  col0 == dj (0-based first
+ * global column), ncols == length(colrange). */
+typedef struct {
+    double *a;
+    int64_t lda;
+    int64_t col0;
+    int64_t ncols;
+} dhqr_oracle_block;
+
+/* S:198-213  _householder_inner!(H, j, Hj): apply (I - v v') to the local columns > j.
+ * Columns are split into nthreads contiguous chunks (S:203-205), one thread per chunk
+ * (S:206), each column doing partialdot then hotloop! over rows j:m (S:208-209). */
+static void householder_inner(const dhqr_oracle_block *blk, int64_t m, int64_t n, int64_t j,
+                              const double *hj, int nthreads) {
+    int64_t lo = j + 1 > blk->col0 ? j + 1 : blk->col0;           /* intersect(j+1:n, colrange) */
+    int64_t hi = blk->col0 + blk->ncols < n ? blk->col0 + blk->ncols : n;
+    if (lo >= hi) return;                                          /* S:202 */
+    int64_t len = hi - lo;
+    int64_t nchunk = (len + nthreads - 1) / nthreads;              /* S:203 */
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+    for (int t = 0; t < nthreads; ++t) {
+        int64_t c0 = lo + (int64_t)t * nchunk;
+        int64_t c1 = c0 + nchunk < hi ? c0 + nchunk : hi;
+        for (int64_t jj = c0; jj < c1; ++jj) {
+            double *col = blk->a + (jj - blk->col0) * blk->lda;
+            double s = dhqr_oracle_partialdot(hj, col, j, m);      /* S:208 */
+            hotloop(col, hj, s, j, m);                             /* S:209 */
+        }
+    }
+}
+
+/* S:122-148  _householder!(H, alpha) run by the owner of block p, fanning the trailing update out
+ * to every block (S:141-143).  S:113-120: owners are visited sequentially in block order. */
+int dhqr_oracle_householder_blocks(int64_t m, int64_t n, int nblocks, const dhqr_oracle_block *blocks,
+                                   double *alpha, int nthreads) {
+    if (m < 0) return -1;
+    if (n < 0 || n > m) return -2;
+    if (nblocks < 1) return -3;
+    if (nthreads < 1) nthreads = dhqr_oracle_max_threads();
+    double *hj = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));    /* S:125 */
+    if (!hj) return -100;
+    for (int p = 0; p < nblocks; ++p) {                            /* S:116 */
+        const dhqr_oracle_block *own = &blocks[p];
+        for (int64_t j = own->col0; j < own->col0 + own->ncols; ++j) {  /* S:127 */
+            double *col = own->a + (j - own->col0) * own->lda;
+            double s = nrm2(col + j, m - j);                       /* S:129 */
+            alpha[j] = s * dhqr_oracle_alphafactor(col[j]);        /* S:130 */
+            double f = 1.0 / sqrt(s * (s + fabs(col[j])));         /* S:131 */
+            col[j] -= alpha[j];                                    /* S:132 */
+            for (int64_t i = j; i < m; ++i) col[i] *= f;           /* S:133-135 */
+            memcpy(hj, col, (size_t)m * sizeof(double));           /* S:138-140 (all m rows) */
+            for (int q = 0; q < nblocks; ++q)                      /* S:141-143 */
+                householder_inner(&blocks[q], m, n, j, hj, nthreads);
+        }
+    }
+    free(hj);
+    return 0;
+}
+
+/* S:311-315  qr!(A) for a plain Matrix: one block holding every column. */
+int dhqr_oracle_qr(int64_t m, int64_t n, double *a, int64_t lda, double *alpha, int nthreads) {
+    if (lda < (m > 1 ? m : 1)) return -4;
+    dhqr_oracle_block b = {a, lda, 0, n};
+    return dhqr_oracle_householder_blocks(m, n, 1, &b, alpha, nthreads);
+}
+
+/* Bounded-sample variant for bench.py's cpu_baseline: runs only column steps [0, jstop) of
+ * S:127 on the full matrix and returns the flops those steps performed (S:129-135 + S:208-209
+ * counted exactly) through *flops. */
+int dhqr_oracle_qr_steps(int64_t m, int64_t n, double *a, int64_t lda, double *alpha, int64_t jstop,
+                         int nthreads, double *flops) {
+    if (lda < (m > 1 ? m : 1)) return -4;
+    if (jstop > n) jstop = n;
+    if (nthreads < 1) nthreads = dhqr_oracle_max_threads();
+    dhqr_oracle_block b = {a, lda, 0, n};
+    double *hj = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+    if (!hj) return -100;
+    double fl = 0.0;
+    for (int64_t j = 0; j < jstop; ++j) {
+        double *col = a + j * lda;
+        double s = nrm2(col + j, m - j);
+        alpha[j] = s * dhqr_oracle_alphafactor(col[j]);
+        double f = 1.0 / sqrt(s * (s + fabs(col[j])));
+        col[j] -= alpha[j];
+        for (int64_t i = j; i < m; ++i) col[i] *= f;
+        memcpy(hj, col, (size_t)m * sizeof(double));
+        householder_inner(&b, m, n, j, hj, nthreads);
+        fl += 3.0 * (double)(m - j) + 4.0 * (double)(m - j) * (double)(n - j - 1);
+    }
+    free(hj);
+    if (flops) *flops = fl;
+    return 0;
+}
+
+/* S:232-242 (and the Vector twin S:215-224)  b <- H_n ... H_1 b = Q'b, owner by owner (S:227-229). */
+int dhqr_oracle_apply_qt_blocks(int64_t m, int64_t n, int nblocks, const dhqr_oracle_block *blocks,
+                                double *b) {
+    for (int p = 0; p < nblocks; ++p) {                            /* S:227 */
+        const dhqr_oracle_block *blk = &blocks[p];
+        int64_t hi = blk->col0 + blk->ncols < n ? blk->col0 + blk->ncols : n;
+        for (int64_t j = blk->col0; j < hi; ++j) {                 /* S:236 */
+            const double *col = blk->a + (j - blk->col0) * blk->lda;
+            double s = dhqr_oracle_partialdot(col, b, j, m);       /* S:237 */
+            for (int64_t i = j; i < m; ++i) b[i] -= col[i] * s;    /* S:238-240 */
+        }
+    }
+    return 0;
+}
+
+/* S:272-282  _solve_householder2_inner!: partial row dot over the block's columns > i. */
+static double solve2_inner(const dhqr_oracle_block *blk, int64_t n, const double *b, int64_t i) {
+    int64_t lo = i + 1 > blk->col0 ? i + 1 : blk->col0;
+    int64_t hi = blk->col0 + blk->ncols < n ? blk->col0 + blk->ncols : n;
+    double bi = 0.0;                                               /* S:276 */
+    for (int64_t j = lo; j < hi; ++j) bi += blk->a[i + (j - blk->col0) * blk->lda] * b[j];  /* S:278-280 */
+    return bi;
+}
+
+/* S:256-270  back-substitution: for i = n..1, sum the partial dots of every block whose last
+ * column is >= i, visiting blocks in reverse order when there is more than one (S:258-259),
+ * then b[i] = (b[i] - sum) / alpha[i] (S:266-267). */
+int dhqr_oracle_backsolve_blocks(int64_t m, int64_t n, int nblocks, const dhqr_oracle_block *blocks,
+                                 const double *alpha, double *b) {
+    (void)m;
+    for (int64_t i = n - 1; i >= 0; --i) {                         /* S:260 */
+        double sum = 0.0;
+        for (int q = nblocks - 1; q >= 0; --q) {                   /* S:259, S:262 */
+            const dhqr_oracle_block *blk = &blocks[q];
+            if (i > blk->col0 + blk->ncols - 1) continue;          /* S:263 */
+            sum += solve2_inner(blk, n, b, i);                     /* S:264, S:266 */
+        }
+        b[i] = (b[i] - sum) / alpha[i];                            /* S:267 */
+    }
+    return 0;
+}
+
+/* S:284-294  solve_householder!(b, H, alpha): Q'b then R^{-1}; x = b[1:n] (S:293). */
+int dhqr_oracle_solve_blocks(int64_t m, int64_t n, int nblocks, const dhqr_oracle_block *blocks,
+                             const double *alpha, double *b) {
+    int rc = dhqr_oracle_apply_qt_blocks(m, n, nblocks, blocks, b);   /* S:288 */
+    if (rc) return rc;
+    return dhqr_oracle_backsolve_blocks(m, n, nblocks, blocks, alpha, b);  /* S:291 */
+}
+
+/* Single-block conveniences (plain Matrix input). */
+int dhqr_oracle_apply_qt(int64_t m, int64_t n, const double *a, int64_t lda, double *b) {
+    dhqr_oracle_block blk = {(double *)a, lda, 0, n};
+    return dhqr_oracle_apply_qt_blocks(m, n, 1, &blk, b);
+}
+int dhqr_oracle_backsolve(int64_t m, int64_t n, const double *a, int64_t lda, const double *alpha, double *b) {
+    dhqr_oracle_block blk = {(double *)a, lda, 0, n};
+    return dhqr_oracle_backsolve_blocks(m, n, 1, &blk, alpha, b);
+}
+/* S:317-321  H \ b: copy b, solve, return the first n entries. */
+int dhqr_oracle_ldiv(int64_t m, int64_t n, const double *a, int64_t lda, const double *alpha,
+                     const double *b, double *x) {
+    double *w = (double *)malloc((size_t)(m > 0 ? m : 1) * sizeof(double));
+    if (!w) return -100;
+    memcpy(w, b, (size_t)m * sizeof(double));                      /* S:318 */
+    dhqr_oracle_block blk = {(double *)a, lda, 0, n};
+    int rc = dhqr_oracle_solve_blocks(m, n, 1, &blk, alpha, w);    /* S:319 */
+    if (!rc) memcpy(x, w, (size_t)n * sizeof(double));             /* S:320 */
+    free(w);
+    return rc;
+}
+
+/* Synthetic inputs: A[i,j] ~ U[0,1) mirroring rand(T,m,n) at test/runtests.jl:45-46.  Julia's
+ * stream cannot be reproduced without Julia, so entries come from a counter-based generator
+ * keyed on (seed, i, j): every rank, the GPU fill kernel and numpy produce bit-identical values. */
+static inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+double dhqr_oracle_uniform(uint64_t seed, uint64_t i, uint64_t j) {
+    uint64_t z = mix64(mix64(seed) ^ (j * 0xD1342543DE82EF95ULL + i));
+    return (double)(z >> 11) * 0x1.0p-53;
+}
+void dhqr_oracle_fill_uniform(uint64_t seed, int64_t i0, int64_t j0, int64_t m, int64_t n, double *a,
+                              int64_t lda) {
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t i = 0; i < m; ++i)
+            a[i + j * lda] = dhqr_oracle_uniform(seed, (uint64_t)(i0 + i), (uint64_t)(j0 + j));
+}
