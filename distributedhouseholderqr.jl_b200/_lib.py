@@ -22,6 +22,8 @@ SIGNATURES = {
     "dhqr_set_option": [_vp, C.c_char_p, _i64],
     "dhqr_get_option": [_vp, C.c_char_p, C.POINTER(_i64)],
     "dhqr_launch_count": [_vp, C.POINTER(_i64)],
+    "dhqr_profile_reset": [_vp],
+    "dhqr_profile_get": [_vp, _int, C.c_char_p, _int, C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_dbl)],
     "dhqr_qr_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _int, _vp],
     "dhqr_apply_qt_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _int, _vp],
     "dhqr_backsolve_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp],
@@ -31,6 +33,7 @@ SIGNATURES = {
     "dhqr_partialdot_f64": [_vp, _vp, _vp, _i64, _i64, _vp, _vp],
     "dhqr_fill_uniform_f64": [_vp, _u64, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
     "dhqr_k_block_reflector_f64": [_vp, _i64, _int, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp],
+    "dhqr_debug_copy_f64": [_vp, C.c_char_p, _vp, _i64, _vp],
     "dhqr_k_panel_f64": [_vp, _i64, _int, _vp, _i64, _vp, _vp],
 }
 

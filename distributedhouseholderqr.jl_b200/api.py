@@ -62,6 +62,25 @@ class Handle:
         _lib.call("dhqr_launch_count", self.raw, C.byref(v))
         return int(v.value)
 
+    def profile_reset(self) -> None:
+        _lib.call("dhqr_profile_reset", self.raw)
+
+    def profile(self) -> dict:
+        """{kernel class: {"ms", "count", "work"}} accumulated since profile_reset() (option "profile" = 1)."""
+        out, i = {}, 0
+        lib = _lib.load()
+        while True:
+            name = C.create_string_buffer(64)
+            ms, cnt, work = C.c_double(), C.c_int64(), C.c_double()
+            rc = lib.dhqr_profile_get(self.raw, i, name, 64, C.byref(ms), C.byref(cnt), C.byref(work))
+            if rc == -2:
+                break
+            if rc != 0:
+                raise _lib.DhqrError("dhqr_profile_get", rc, lib.dhqr_last_error().decode())
+            out[name.value.decode()] = {"ms": ms.value, "count": cnt.value, "work": work.value}
+            i += 1
+        return out
+
     def close(self) -> None:
         if self._h:
             _lib.load().dhqr_destroy(self._h)

@@ -121,6 +121,13 @@ struct dhqr_context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // kernel attribute state
     bool attrs_set = false;
+    // per-kernel-class CUDA-event profiling (option "profile")
+    int profile = 0;
+    struct ProfRec { int slot; cudaEvent_t e0, e1; };
+    struct ProfSlot { const char* name; double ms = 0.0; int64_t count = 0; double work = 0.0; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<ProfSlot> prof_slots;
+    cudaEvent_t prof_open = nullptr;
 };
 
 static constexpr int NBMAX = 128;
@@ -188,8 +195,32 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
     return 0;
 }
 
-static int post(dhqr_context* c, cudaStream_t st, const char* what) {
+static int prof_slot(dhqr_context* c, const char* name) {
+    for (size_t i = 0; i < c->prof_slots.size(); ++i)
+        if (!strcmp(c->prof_slots[i].name, name)) return (int)i;
+    dhqr_context::ProfSlot s;
+    s.name = name;
+    c->prof_slots.push_back(s);
+    return (int)c->prof_slots.size() - 1;
+}
+// pre(): open a CUDA-event bracket on the launching stream when profiling is on
+static void pre(dhqr_context* c, cudaStream_t st) {
+    if (!c->profile) return;
+    cudaEventCreate(&c->prof_open);
+    cudaEventRecord(c->prof_open, st);
+}
+static int post(dhqr_context* c, cudaStream_t st, const char* what, double work = 0.0) {
     c->launches++;
+    if (c->profile && c->prof_open) {
+        dhqr_context::ProfRec r;
+        r.slot = prof_slot(c, what);
+        r.e0 = c->prof_open;
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e1, st);
+        c->prof_pending.push_back(r);
+        c->prof_slots[r.slot].work += work;
+        c->prof_open = nullptr;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(1000 + (int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
     if (c->sync) {
@@ -233,25 +264,29 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g1.a_aligned = (((uintptr_t)C & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
     g1.Wp = c->wpart; g1.pstride = pstride;
     dim3 grid1(tiles, nsplit);
+    pre(c, st);
     if (small) {
         K_G1_32<<<grid1, (1 * 4 + 1) * 32, smem_g1(32, G1S_BN, G1S_STAGES), st>>>(g1);
     } else {
         K_G1_128<<<grid1, (4 * 2 + 1) * 32, smem_g1(128, G1_BN, G1_STAGES), st>>>(g1);
     }
-    TRY(post(c, st, "k_gemm_vta"));
+    TRY(post(c, st, small ? "k_gemm_vta32" : "k_gemm_vta128", 2.0 * (double)rows * nbp * ((double)ncols + nbp)));
+    pre(c, st);
     if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(c->wpart, pstride, nsplit, c->linv);
     else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(c->wpart, pstride, nsplit, c->linv);
     TRY(post(c, st, "k_tinv"));
+    pre(c, st);
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
     if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
     else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
     TRY(post(c, st, "k_ymake"));
+    pre(c, st);
     GemmCvyArgs g2;
     g2.C = C; g2.ldc = ldc; g2.rows = rows; g2.row_lo = row_lo; g2.ncols = ncols;
     g2.V = Vcols; g2.ldv = c->ldv; g2.Y = c->ybuf; g2.ldy = NBPK; g2.nbp = small ? 32 : (int)rup(nbp, KC);
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
     K_G2<<<grid2, (2 * 2 + 1) * 32, smem_g2(), st>>>(g2);
-    TRY(post(c, st, "k_gemm_cvy"));
+    TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
     return 0;
 }
 
@@ -274,10 +309,11 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* P, int64_t ldp
     a.rows_per_cta = (int)rpc; a.lds = lds;
     a.part = c->ppart; a.piv = c->ppiv; a.bar = c->bar; a.bar_base = c->bar_count;
     void* args[] = {&a};
+    pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
     if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_panel failed: %s", cudaGetErrorString(e));
     c->bar_count += (unsigned long long)G * ncols;
-    return post(c, st, "k_panel");
+    return post(c, st, "k_panel", 16.0 * (double)mp * ncols);   // work = bytes: panel read once + written once
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -533,6 +569,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->panel_ctas = (int)value;
     } else if (!strcmp(key, "sync")) {
         c->sync = value ? 1 : 0;
+    } else if (!strcmp(key, "profile")) {
+        c->profile = value ? 1 : 0;
     } else {
         return set_err(-2, "unknown option '%s'", key);
     }
@@ -546,6 +584,7 @@ int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
     if (!strcmp(key, "nb")) *value = c->nb;
     else if (!strcmp(key, "panel_ctas")) *value = c->panel_ctas;
     else if (!strcmp(key, "sync")) *value = c->sync;
+    else if (!strcmp(key, "profile")) *value = c->profile;
     else if (!strcmp(key, "sms")) *value = c->sms;
     else if (!strcmp(key, "rank")) *value = c->rank;
     else if (!strcmp(key, "nranks")) *value = c->nranks;
@@ -557,6 +596,39 @@ int dhqr_launch_count(dhqr_handle c, int64_t* count) {
     if (!c) return set_err(-1, "null handle");
     if (!count) return set_err(-2, "null count");
     *count = c->launches;
+    return 0;
+}
+
+static int prof_drain(dhqr_context* c) {
+    for (auto& r : c->prof_pending) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(r.e1));
+        CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        c->prof_slots[r.slot].ms += ms;
+        c->prof_slots[r.slot].count += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c->prof_pending.clear();
+    return 0;
+}
+
+int dhqr_profile_reset(dhqr_handle c) {
+    if (!c) return set_err(-1, "null handle");
+    TRY(prof_drain(c));
+    for (auto& s : c->prof_slots) { s.ms = 0.0; s.count = 0; s.work = 0.0; }
+    return 0;
+}
+
+int dhqr_profile_get(dhqr_handle c, int index, char* name, int name_len, double* ms, int64_t* count, double* work) {
+    if (!c) return set_err(-1, "null handle");
+    TRY(prof_drain(c));
+    if (index < 0 || index >= (int)c->prof_slots.size()) return set_err(-2, "index out of range");
+    const auto& s = c->prof_slots[index];
+    if (name && name_len > 0) { strncpy(name, s.name, name_len - 1); name[name_len - 1] = 0; }
+    if (ms) *ms = s.ms;
+    if (count) *count = s.count;
+    if (work) *work = s.work;
     return 0;
 }
 
@@ -729,6 +801,22 @@ int dhqr_k_block_reflector_f64(dhqr_handle c, int64_t rows, int nbp, const doubl
                          cudaMemcpyDeviceToDevice, st));
     TRY(apply_block_reflector(c, st, c->vbuf, nbk, rows, row_lo, dC, ldc, ncols));
     if (d_linv_out) CU(cudaMemcpyAsync(d_linv_out, c->linv, sizeof(double) * (size_t)nbk * nbk, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t nelems, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (!which) return set_err(-2, "null name");
+    if (!d_dst) return set_err(-3, "null destination");
+    const double* src = nullptr;
+    size_t have = 0;
+    if (!strcmp(which, "wpart")) { src = c->wpart; have = c->wpart_elems; }
+    else if (!strcmp(which, "ybuf")) { src = c->ybuf; have = c->ybuf_elems; }
+    else if (!strcmp(which, "linv")) { src = c->linv; have = (size_t)NBMAX * NBMAX; }
+    else if (!strcmp(which, "vbuf")) { src = c->vbuf; have = c->vbuf_elems; }
+    else return set_err(-2, "unknown buffer '%s'", which);
+    if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);
+    CU(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)nelems, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

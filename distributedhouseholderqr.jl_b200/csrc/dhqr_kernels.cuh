@@ -63,6 +63,19 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// Consumer-side release of the PREVIOUS stage, called right after the wait for the current one.
+// Releasing stage s at the end of its own chunk is not safe: ptxas hoists the arrive above the last
+// DMMAs, i.e. directly behind the last LDS of the stage, and the TMA producer (async proxy) can then
+// overwrite the buffer while that read is still in flight (observed: 8x32 blocks of C wrong once per
+// ~5e6 CTAs).  One iteration later every DMMA of the previous chunk has issued, hence every LDS it
+// depends on has returned.  Costs nothing: the producer refills the stage during the current chunk.
+__device__ __forceinline__ void release_prev_stage(uint64_t* empty, int it, int stages, int lane) {
+    if (it > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[(it - 1) % stages]);
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -177,6 +190,7 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs 
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
+        release_prev_stage(empty, it, STAGES, lane);
         const double* v = sV + (size_t)s * NBP * LDK + wm * WTM * LDK + frag;
         const double* b = sB + (size_t)s * BN * LDK + wn * WTN * LDK + frag;
 #pragma unroll
@@ -191,8 +205,6 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs 
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
     }
     double* out = a.Wp + (int64_t)blockIdx.y * a.pstride;
 #pragma unroll
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyAr
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
+        release_prev_stage(empty, it, STAGES, lane);
         const double* v = sV + (size_t)s * KC * LDV + wm * WTM + fragA;
         const double* y = sY + (size_t)s * BN * LDK + wn * WTN * LDK + fragB;
 #pragma unroll
@@ -306,8 +319,6 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyAr
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
     }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {

@@ -54,11 +54,18 @@ int dhqr_nccl_unique_id(void *out_unique_id);
 int dhqr_destroy(dhqr_handle h);
 /* Tunables: "nb" (outer panel width, multiple of 32 in [32,128], default 128), "panel_ctas"
  * (CTAs of the cooperative panel kernel, 0 = one per SM), "sync" (1 = cudaStreamSynchronize and
- * error-check after every entry point; debugging). */
+ * error-check after every kernel launch; debugging), "profile" (1 = CUDA-event bracket per launch). */
 int dhqr_set_option(dhqr_handle h, const char *key, int64_t value);
 int dhqr_get_option(dhqr_handle h, const char *key, int64_t *value);
 /* Number of kernel launches enqueued by this handle since creation (bench.py: gpu_launches). */
 int dhqr_launch_count(dhqr_handle h, int64_t *count);
+/* Per-kernel-class timing with CUDA events on the launching stream (option "profile" = 1 turns the
+ * brackets on; the reference keeps the same kind of accumulators as t1a/t1b/t2, S:126-146, S:291).
+ * dhqr_profile_get returns slot `index` (0.. until -2): class name, accumulated milliseconds, launch
+ * count and algorithmic work (flops for the GEMM classes, bytes for the panel).  Blocks on the events. */
+int dhqr_profile_reset(dhqr_handle h);
+int dhqr_profile_get(dhqr_handle h, int index, char *name, int name_len, double *ms, int64_t *count,
+                     double *work);
 
 /* ---- qr!  (S:311-315 -> householder! S:113-120 -> _householder! S:122-148 -> _householder_inner!
  *            S:198-213 with partialdot S:42-49 and hotloop! S:156-160) --------------------------
@@ -112,6 +119,8 @@ int dhqr_fill_uniform_f64(dhqr_handle h, uint64_t seed, int64_t i0, int64_t j0, 
 int dhqr_k_block_reflector_f64(dhqr_handle h, int64_t rows, int nbp, const double *dV, int64_t ldv,
                                int64_t row_lo, int ncols, double *dC, int64_t ldc, double *d_linv_out,
                                void *stream);
+/* Copy an internal workspace buffer ("wpart", "ybuf", "linv", "vbuf") to d_dst (debugging / tests). */
+int dhqr_debug_copy_f64(dhqr_handle h, const char *which, double *d_dst, int64_t nelems, void *stream);
 /* Panel kernel: factor the rows x ncols (ncols <= 32) panel at dP in place (reference recurrences
  * S:127-135 + S:208-209 restricted to the panel), alpha -> d_alpha[0:ncols]. */
 int dhqr_k_panel_f64(dhqr_handle h, int64_t rows, int ncols, double *dP, int64_t ldp, double *d_alpha,

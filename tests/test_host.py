@@ -1,0 +1,46 @@
+"""Host-side mirror of the reference interface: layout and partition logic (no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+import dhqr_b200 as D
+
+
+def test_splits_match_darray_default_distribution():
+    # DistributedArrays defaultdist: even chunks, remainder to the first blocks (T:71 uses (1, nworkers()))
+    assert D.splits(2, 100) == [0, 50, 100]
+    assert D.splits(4, 4096) == [0, 1024, 2048, 3072, 4096]
+    assert D.splits(3, 10) == [0, 4, 7, 10]
+    assert D.splits(8, 8192)[-1] == 8192 and len(D.splits(8, 8192)) == 9
+    for P in range(1, 9):
+        b = D.splits(P, 103)
+        assert b[0] == 0 and b[-1] == 103 and all(0 <= b[i + 1] - b[i] <= 103 // P + 1 for i in range(P))
+
+
+def test_colmajor_helpers_cpu():
+    A = D.colmajor_empty(5, 3, device="cpu")
+    assert A.shape == (5, 3) and A.stride() == (1, 5)
+    B = D.colmajor_empty(5, 3, device="cpu", lda=8)
+    assert B.stride() == (1, 8)
+    x = np.arange(12.0).reshape(4, 3)
+    C = D.to_colmajor(x, device="cpu")
+    assert C.stride() == (1, 4) and np.array_equal(C.numpy(), x)
+
+
+def test_local_column_block_indexing():
+    # LocalColumnBlock (S:26-40): global column j lives at local column j - dj
+    Al = D.to_colmajor(np.arange(20.0).reshape(4, 5), device="cpu")
+    blk = D.LocalColumnBlock(Al, 10, range(10, 15))
+    assert torch.equal(blk.global_col(12), Al[:, 2])
+
+
+def test_alphafactor():
+    assert D.alphafactor(3.0) == -1.0 and D.alphafactor(-2.0) == 1.0 and D.alphafactor(0.0) == 0.0
+
+
+def test_rejects_row_major_and_wrong_dtype():
+    from dhqr_b200.api import _lda
+    with pytest.raises(ValueError):
+        _lda(torch.zeros(4, 3, dtype=torch.float64))            # row-major
+    with pytest.raises(TypeError):
+        _lda(D.colmajor_empty(4, 3, device="cpu").float())

@@ -53,9 +53,10 @@ check("partialdot", t_pdot)
 
 def block_reflector_case(rows, nbp, ncols, row_lo, ld_extra=0, seed=0):
     g = torch.Generator(device="cpu"); g.manual_seed(seed)
-    V = torch.rand(rows, nbp, dtype=torch.float64, generator=g) - 0.5
-    V = torch.tril(V)                      # lower trapezoid like a Householder block
-    V[:row_lo] = 0.0
+    # a genuine Householder block (|v|^2 = 2): V = tril of the oracle's factorisation of a random panel
+    Hp, _ = O.np_qr(O.np_uniform(seed + 11, rows - row_lo, nbp))
+    V = torch.zeros(rows, nbp, dtype=torch.float64)
+    V[row_lo:] = torch.from_numpy(np.tril(Hp))
     Cm = torch.rand(rows, ncols, dtype=torch.float64, generator=g)
     dV = D.to_colmajor(V, dev)
     dC = D.colmajor_empty(rows, ncols, dev, lda=rows + ld_extra); dC.copy_(Cm)
