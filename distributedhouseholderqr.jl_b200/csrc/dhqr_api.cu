@@ -103,19 +103,18 @@ struct dhqr_context {
     // options
     int nb = 128, panel_ctas = 0, sync = 0;
     // workspace
-    double* vbuf = nullptr;  size_t vbuf_elems = 0;  int64_t ldv = 0;   // packed V block  [NBMAX][ldv]
+    double* vpk = nullptr;   size_t vpk_elems = 0;   int64_t vrows_cap = 0;   // packed V block [chunk][128][68]
     double* wpart = nullptr; size_t wpart_elems = 0;                    // gemm_vta partials
-    double* ybuf = nullptr;  size_t ybuf_elems = 0;                     // Y = -T'W
+    double* wsum = nullptr;  size_t wsum_elems = 0;                     // reduced Wext
+    double* ypk = nullptr;   size_t ypk_elems = 0;                      // packed Y = -T'W
     double* linv = nullptr;                                             // [128*128]
-    double* ppart = nullptr; size_t ppart_elems = 0;                    // panel partials [2][G][IB]
-    double* ppiv = nullptr;                                             // [2][IB]
+    unsigned long long* cells = nullptr;                                // panel exchange cells [IB+1][MAXG+1][IB][2]
+    uint32_t ll_epoch = 0;
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
     double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
     double* hostB = nullptr; size_t hostB_elems = 0;
     int64_t* d_i64 = nullptr;                                           // small int64 scratch (partition exchange)
-    unsigned long long* bar = nullptr;
-    unsigned long long bar_count = 0;
     int64_t launches = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -134,23 +133,23 @@ static constexpr int NBMAX = 128;
 static constexpr int MAXCTAS_FACTOR = 3;
 
 // gemm tile configurations
-static constexpr int G1_BN = 64, G1_STAGES = 4;             // gemm_vta<128>: 128 x 64 tile, 8+1 warps
-static constexpr int G1S_BN = 128, G1S_STAGES = 4;          // gemm_vta<32> : 32 x 128 tile, 4+1 warps
-static constexpr int G2_BM = 128, G2_BN = 64, G2_STAGES = 2;  // gemm_cvy: 128 x 64 tile, 4+1 warps, 2 CTAs/SM
+static constexpr int G1_BN = 64, G1_NPW = 2;                // gemm_vta<128>: 128 x 64 tile, 8 MMA + 2 TMA warps
+static constexpr int G1S_BN = 128, G1S_NPW = 4;             // gemm_vta<32> : 32 x 128 tile, 4 MMA + 4 TMA warps
+static constexpr int G2_BM = 128, G2_BN = YT;               // gemm_cvy: 128 x 64 tile, 4 MMA + 1 TMA warps, 2 CTAs/SM
 
-static size_t smem_g1(int nbp, int bn, int stages) { return (size_t)stages * (nbp + bn) * LDK * 8 + 2 * stages * 8; }
-static size_t smem_g2() { return (size_t)G2_STAGES * (KC * (G2_BM + 4) + G2_BN * LDK) * 8 + 2 * G2_STAGES * 8; }
+static size_t smem_g1(int nbp, int bn) { return (size_t)2 * (nbp + bn) * LD1 * 8 + 4 * 8; }
+static size_t smem_g2() { return (size_t)2 * (2 * KC * LD1 + G2_BN * LDK) * 8 + 4 * 8; }
 static size_t smem_tinv(int nbp) { return ((size_t)nbp * (nbp + 1) + 4 * 32 * 33) * 8; }
 static size_t smem_ymake(int nbp) { return ((size_t)nbp * nbp + YCOLS * nbp) * 8; }
 
-#define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_STAGES>
-#define K_G1_32 k_gemm_vta<32, G1S_BN, 1, 4, G1S_STAGES>
-#define K_G2 k_gemm_cvy<G2_BM, G2_BN, 2, 2, G2_STAGES, 2>
+#define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_NPW>
+#define K_G1_32 k_gemm_vta<32, G1S_BN, 1, 4, G1S_NPW>
+#define K_G2 k_gemm_cvy<2>
 
 static int set_attrs(dhqr_context* c) {
     if (c->attrs_set) return 0;
-    CU(cudaFuncSetAttribute(K_G1_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(128, G1_BN, G1_STAGES)));
-    CU(cudaFuncSetAttribute(K_G1_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(32, G1S_BN, G1S_STAGES)));
+    CU(cudaFuncSetAttribute(K_G1_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(128, G1_BN)));
+    CU(cudaFuncSetAttribute(K_G1_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(32, G1S_BN)));
     CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
@@ -177,19 +176,19 @@ static int ensure(T** p, size_t* have, size_t need) {
 
 static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
     TRY(set_attrs(c));
-    const int64_t ldv = rup(m, 128) + 128;
-    if (c->ldv < ldv || !c->vbuf) {
-        TRY(ensure(&c->vbuf, &c->vbuf_elems, (size_t)ldv * NBMAX));
-        c->ldv = ldv;
+    const int64_t vrows = rup(m, 128) + 128;
+    if (c->vrows_cap < vrows || !c->vpk) {
+        TRY(ensure(&c->vpk, &c->vpk_elems, (size_t)(vrows / KC1) * VPK_CHUNK));
+        c->vrows_cap = vrows;
     }
     const int64_t maxctas = (int64_t)MAXCTAS_FACTOR * c->sms;
     const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
     TRY(ensure(&c->wpart, &c->wpart_elems, (size_t)std::max(maxctas, tiles_max) * NBMAX * G1S_BN + (size_t)NBMAX * G1S_BN));
-    TRY(ensure(&c->ybuf, &c->ybuf_elems, (size_t)NBMAX * (rup(n_local_max, 128) + 128)));
+    TRY(ensure(&c->wsum, &c->wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
+    TRY(ensure(&c->ypk, &c->ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
     size_t one = 0;
     if (!c->linv) { one = 0; TRY(ensure(&c->linv, &one, (size_t)NBMAX * NBMAX)); }
-    TRY(ensure(&c->ppart, &c->ppart_elems, (size_t)2 * c->sms * IB));
-    if (!c->ppiv) { one = 0; TRY(ensure(&c->ppiv, &one, (size_t)2 * IB)); }
+    if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)(IB + 1) * (PANEL_MAXG + 1) * IB * 2)); c->ll_epoch = 0; }
     TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
     return 0;
@@ -246,46 +245,53 @@ static int pick_splits(int tiles, int nchunks, int sms) {
     return best;
 }
 
-static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* Vcols, int nbp, int64_t rows,
-                                 int64_t row_lo, double* C, int64_t ldc, int ncols) {
+static int apply_block_reflector(dhqr_context* c, cudaStream_t st, int voff, int nbp, int64_t rows, int64_t row_lo,
+                                 double* C, int64_t ldc, int ncols) {
+    // V = packed columns [voff, voff + nbp) of c->vpk (columns beyond the live ones are zero)
     if (ncols <= 0 || rows <= 0) return 0;
     const bool small = (nbp <= 32);
-    const int NBPK = small ? 32 : 128;          // kernel instantiation (V columns beyond nbp are zero)
+    const int NBPK = small ? 32 : 128;          // kernel instantiation
     const int bn = small ? G1S_BN : G1_BN;
     const int next = NBPK + ncols;
     const int tiles = (next + bn - 1) / bn;
-    const int nchunks = (int)((rows + KC - 1) / KC);
+    const int nchunks = (int)((rows + KC1 - 1) / KC1);
     const int nsplit = pick_splits(tiles, nchunks, c->sms);
     const int64_t pstride = (int64_t)tiles * bn * NBPK;
     if ((size_t)(pstride * nsplit) > c->wpart_elems) return set_err(4001, "internal: W partial workspace too small");
+    if ((size_t)next * NBPK > c->wsum_elems) return set_err(4003, "internal: W workspace too small");
     GemmVtaArgs g1;
-    g1.V = Vcols; g1.ldv = c->ldv; g1.nv = NBPK;
+    g1.vpk = c->vpk; g1.voff = voff; g1.nv = NBPK;
     g1.A = C; g1.lda = ldc; g1.rows = rows; g1.na = ncols; g1.nchunks = nchunks;
     g1.a_aligned = (((uintptr_t)C & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
     g1.Wp = c->wpart; g1.pstride = pstride;
     dim3 grid1(tiles, nsplit);
     pre(c, st);
     if (small) {
-        K_G1_32<<<grid1, (1 * 4 + 1) * 32, smem_g1(32, G1S_BN, G1S_STAGES), st>>>(g1);
+        K_G1_32<<<grid1, (1 * 4 + G1S_NPW) * 32, smem_g1(32, G1S_BN), st>>>(g1);
     } else {
-        K_G1_128<<<grid1, (4 * 2 + 1) * 32, smem_g1(128, G1_BN, G1_STAGES), st>>>(g1);
+        K_G1_128<<<grid1, (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
     }
     TRY(post(c, st, small ? "k_gemm_vta32" : "k_gemm_vta128", 2.0 * (double)rows * nbp * ((double)ncols + nbp)));
     pre(c, st);
-    if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(c->wpart, pstride, nsplit, c->linv);
-    else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(c->wpart, pstride, nsplit, c->linv);
-    TRY(post(c, st, "k_tinv"));
+    const int64_t nelem = (int64_t)next * NBPK;
+    k_wreduce<<<(unsigned)std::min<int64_t>((nelem + 255) / 256, 8 * c->sms), 256, 0, st>>>(c->wpart, pstride, nsplit, nelem, c->wsum);
+    TRY(post(c, st, "k_wreduce"));
+    pre(c, st);
+    if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(c->wsum, c->linv);
+    else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(c->wsum, c->linv);
+    TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
     pre(c, st);
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
-    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
-    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(c->wpart, pstride, nsplit, NBPK, ncols, c->linv, c->ybuf, NBPK);
-    TRY(post(c, st, "k_ymake"));
+    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(c->wsum, ncols, c->linv, c->ypk);
+    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(c->wsum, ncols, c->linv, c->ypk);
+    TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
     pre(c, st);
     GemmCvyArgs g2;
     g2.C = C; g2.ldc = ldc; g2.rows = rows; g2.row_lo = row_lo; g2.ncols = ncols;
-    g2.V = Vcols; g2.ldv = c->ldv; g2.Y = c->ybuf; g2.ldy = NBPK; g2.nbp = small ? 32 : (int)rup(nbp, KC);
+    g2.vpk = c->vpk; g2.voff = voff; g2.ypk = c->ypk;
+    g2.nkq = small ? 1 : (int)(rup(nbp, KC) / KC); g2.nkq_alloc = NBPK / KC;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
-    K_G2<<<grid2, (2 * 2 + 1) * 32, smem_g2(), st>>>(g2);
+    K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
     TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
     return 0;
 }
@@ -294,25 +300,33 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
 // cooperative panel launch: factor mp x ncols (<= IB) at P, V block -> vout columns
 // ------------------------------------------------------------------------------------------------
 static int launch_panel(dhqr_context* c, cudaStream_t st, double* P, int64_t ldp, int64_t mp, int ncols, double* alpha,
-                        double* vout, int64_t vtop, int64_t vrows) {
-    int gmax = c->panel_ctas > 0 ? std::min(c->panel_ctas, c->sms) : c->sms;
+                        int voff, int64_t vtop, int64_t vrows, bool write_v = true) {
+    int gmax = c->panel_ctas > 0 ? c->panel_ctas : 96;
+    gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
+    while ((size_t)IB * ((size_t)rpc | 1) * 8 > 200 * 1024 && gmax < std::min(c->sms, PANEL_MAXG)) {   // slab too big: use more CTAs
+        gmax = std::min(gmax * 2, std::min(c->sms, PANEL_MAXG));
+        rpc = rup(std::max<int64_t>((mp + gmax - 1) / gmax, 64), 8);
+    }
     const int G = (int)((mp + rpc - 1) / rpc);
     const int lds = (int)rpc | 1;
     const size_t smem = (size_t)IB * lds * 8;
     if (smem > 200 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
-    if ((size_t)2 * G * IB > c->ppart_elems) return set_err(4002, "internal: panel partial workspace too small");
+    if (c->ll_epoch > 0xF0000000u) {   // tag space nearly used up: start over with clean cells
+        CU(cudaMemsetAsync(c->cells, 0, sizeof(unsigned long long) * (size_t)(IB + 1) * (PANEL_MAXG + 1) * IB * 2, st));
+        c->ll_epoch = 0;
+    }
     PanelArgs a;
     a.P = P; a.ldp = ldp; a.mp = mp; a.ncols = ncols; a.alpha = alpha;
-    a.Vout = vout; a.ldv = c->ldv; a.vtop = vtop; a.vrows = vrows;
+    a.vpk = write_v ? c->vpk : nullptr; a.voff = voff; a.vtop = vtop; a.vrows = vrows;
     a.rows_per_cta = (int)rpc; a.lds = lds;
-    a.part = c->ppart; a.piv = c->ppiv; a.bar = c->bar; a.bar_base = c->bar_count;
+    a.cells = c->cells; a.epoch = c->ll_epoch;
     void* args[] = {&a};
     pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
     if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_panel failed: %s", cudaGetErrorString(e));
-    c->bar_count += (unsigned long long)G * ncols;
+    c->ll_epoch += IB + 1;
     return post(c, st, "k_panel", 16.0 * (double)mp * ncols);   // work = bytes: panel read once + written once
 }
 
@@ -388,24 +402,25 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
                 const int ib = std::min(IB, p.kb - o);
                 const int64_t cs = p.c + o;                                   // global column == pivot row
                 double* P = A + (cs - col0) * lda + cs;
-                TRY(launch_panel(c, st, P, lda, m - cs, ib, alpha + cs, c->vbuf + (int64_t)o * c->ldv, cs - r0, vrows));
+                TRY(launch_panel(c, st, P, lda, m - cs, ib, alpha + cs, o, cs - r0, vrows));
                 const int rem = p.kb - (o + ib);
                 if (rem > 0)   // update the rest of the outer panel with this sub-panel's reflectors
-                    TRY(apply_block_reflector(c, st, c->vbuf + (int64_t)o * c->ldv, IB, rows, cs - r0,
-                                              A + (cs + ib - col0) * lda + r0, lda, rem));
+                    TRY(apply_block_reflector(c, st, o, IB, rows, cs - r0, A + (cs + ib - col0) * lda + r0, lda, rem));
             }
-            if (nbp > IB && nbp < NBMAX)   // zero the V columns the 128-wide kernels read beyond nbp
-                CU(cudaMemsetAsync(c->vbuf + (int64_t)nbp * c->ldv, 0, sizeof(double) * (size_t)(NBMAX - nbp) * c->ldv, st));
+            if (nbp > IB && nbp < NBMAX) {   // zero the V columns the 128-wide kernels read beyond nbp
+                k_vpk_zero_cols<<<2 * c->sms, 256, 0, st>>>(c->vpk, vrows / KC1, nbp, NBMAX);
+                TRY(post(c, st, "k_vpk_zero_cols"));
+            }
         }
         if (c->nranks > 1) {
             // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
-            NC(g_nccl.Broadcast(c->vbuf, c->vbuf, (size_t)c->ldv * (nbp > IB ? NBMAX : IB), ncclFloat64, p.owner, c->comm, st));
+            NC(g_nccl.Broadcast(c->vpk, c->vpk, (size_t)(vrows / KC1) * VPK_CHUNK, ncclFloat64, p.owner, c->comm, st));
             NC(g_nccl.Broadcast(alpha + p.c, alpha + p.c, (size_t)p.kb, ncclFloat64, p.owner, c->comm, st));
         }
         // trailing update of the local columns right of the panel (S:198-213 for nb columns at once)
         const int64_t t0 = std::max(p.c + p.kb, col0);
         if (t0 < lend)
-            TRY(apply_block_reflector(c, st, c->vbuf, nbp, rows, p.c - r0, A + (t0 - col0) * lda + r0, lda, (int)(lend - t0)));
+            TRY(apply_block_reflector(c, st, 0, nbp, rows, p.c - r0, A + (t0 - col0) * lda + r0, lda, (int)(lend - t0)));
     }
     return 0;
 }
@@ -465,9 +480,9 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
         const int64_t rows = m - r0, vrows = rup(rows, 128);
         const int nbp = kb <= IB ? IB : NBMAX;
         dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbp);
-        k_pack_v<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, c->vbuf, c->ldv, cs - r0, vrows, nbp);
-        TRY(post(c, st, "k_pack_v"));
-        TRY(apply_block_reflector(c, st, c->vbuf, nbp, rows, cs - r0, b + r0, ldb, nrhs));
+        k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk, 0, cs - r0, vrows);
+        TRY(post(c, st, "k_pack"));
+        TRY(apply_block_reflector(c, st, 0, nbp, rows, cs - r0, b + r0, ldb, nrhs));
     }
     return 0;
 }
@@ -506,8 +521,6 @@ static int create_common(dhqr_handle* h, int device) {
     dhqr_context* c = new dhqr_context();
     c->device = device;
     c->sms = prop.multiProcessorCount;
-    CU(cudaMalloc((void**)&c->bar, 64));
-    CU(cudaMemset(c->bar, 0, 64));
     CU(cudaMalloc((void**)&c->d_i64, sizeof(int64_t) * 2 * 1025));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev0, cudaEventDisableTiming));
@@ -549,8 +562,8 @@ int dhqr_destroy(dhqr_handle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    cudaFree(c->vbuf); cudaFree(c->wpart); cudaFree(c->ybuf); cudaFree(c->linv); cudaFree(c->ppart); cudaFree(c->ppiv);
-    cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64); cudaFree(c->bar);
+    cudaFree(c->vpk); cudaFree(c->wpart); cudaFree(c->wsum); cudaFree(c->ypk); cudaFree(c->linv); cudaFree(c->cells);
+    cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -796,10 +809,11 @@ int dhqr_k_block_reflector_f64(dhqr_handle c, int64_t rows, int nbp, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(c, rows, ncols));
     const int nbk = nbp <= IB ? IB : NBMAX;
-    CU(cudaMemsetAsync(c->vbuf, 0, sizeof(double) * (size_t)c->ldv * nbk, st));
-    CU(cudaMemcpy2DAsync(c->vbuf, (size_t)c->ldv * 8, dV, (size_t)ldv * 8, (size_t)rows * 8, (size_t)nbp,
-                         cudaMemcpyDeviceToDevice, st));
-    TRY(apply_block_reflector(c, st, c->vbuf, nbk, rows, row_lo, dC, ldc, ncols));
+    const int64_t vrows = rup(rows, 128);
+    dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbk);
+    k_pack<<<grid, 256, 0, st>>>(dV, ldv, rows, nbp, 0, c->vpk, 0, 0, vrows);
+    TRY(post(c, st, "k_pack"));
+    TRY(apply_block_reflector(c, st, 0, nbk, rows, row_lo, dC, ldc, ncols));
     if (d_linv_out) CU(cudaMemcpyAsync(d_linv_out, c->linv, sizeof(double) * (size_t)nbk * nbk, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -811,9 +825,10 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     const double* src = nullptr;
     size_t have = 0;
     if (!strcmp(which, "wpart")) { src = c->wpart; have = c->wpart_elems; }
-    else if (!strcmp(which, "ybuf")) { src = c->ybuf; have = c->ybuf_elems; }
+    else if (!strcmp(which, "wsum")) { src = c->wsum; have = c->wsum_elems; }
+    else if (!strcmp(which, "ypk")) { src = c->ypk; have = c->ypk_elems; }
     else if (!strcmp(which, "linv")) { src = c->linv; have = (size_t)NBMAX * NBMAX; }
-    else if (!strcmp(which, "vbuf")) { src = c->vbuf; have = c->vbuf_elems; }
+    else if (!strcmp(which, "vpk")) { src = c->vpk; have = c->vpk_elems; }
     else return set_err(-2, "unknown buffer '%s'", which);
     if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);
     CU(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)nelems, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -830,7 +845,7 @@ int dhqr_k_panel_f64(dhqr_handle c, int64_t rows, int ncols, double* dP, int64_t
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(c, rows, ncols));
-    return launch_panel(c, st, dP, ldp, rows, ncols, d_alpha, c->vbuf, 0, rup(rows, 128));
+    return launch_panel(c, st, dP, ldp, rows, ncols, d_alpha, 0, 0, rup(rows, 128));
 }
 
 }  // extern "C"

@@ -83,38 +83,59 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// gemm_vta:  Wext(NBP x next) = V' * [V(:,0:nv) | A]      "TN", reduction over the long row dimension
-//   V   : ldv x NBP packed Householder block (rows = window rows, zero above the diagonal and in
-//         the padding rows), always full KC-row chunks.
-//   A   : trailing columns (user storage), `rows` valid rows; the last chunk may be ragged.
+// Packed operand layouts (handle-owned buffers, written by k_panel / k_pack / k_ymake)
+//   vpk : Householder block V of the current outer panel, 64-row chunks, each chunk stored exactly as
+//         the padded shared-memory tile the GEMMs want:   vpk[q][col][LD1],  q = window_row / 64,
+//         col in [0,128), LD1 = 68 (68 % 16 == 4 -> conflict-free DMMA fragment loads).
+//         => gemm_vta stages a whole V chunk, and gemm_cvy a 64 x 32 slice, with ONE TMA bulk copy.
+//   ypk : Y = -T'W,  ypk[n_tile][k_chunk][64 cols][LDK]  -> one bulk copy per gemm_cvy stage.
+// (Issuing one 256 B bulk copy per column and stage made gemm_vta TMA-issue bound at 36 % of peak.)
+// ------------------------------------------------------------------------------------------------
+constexpr int KC1 = 64;                    // rows per gemm_vta stage
+constexpr int LD1 = KC1 + 4;               // 68
+constexpr int VPK_COLS = 128;
+constexpr int VPK_CHUNK = VPK_COLS * LD1;  // doubles per 64-row chunk
+constexpr int YT = 64;                     // ypk column-tile width (== gemm_cvy BN)
+
+__device__ __host__ __forceinline__ int64_t vpk_index(int64_t wrow, int col) {
+    return ((wrow >> 6) * VPK_COLS + col) * LD1 + (wrow & 63);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_vta:  Wext(NBP x next) = V' * [V | A]      "TN", reduction over the long row dimension
+//   V   : NBP packed columns [voff, voff+NBP) of vpk; one bulk copy per 64-row chunk.
+//   A   : trailing columns in user storage, `rows` valid rows, 512 B bulk copy per column and chunk
+//         (generic loads for a ragged tail or unaligned storage), spread over NPW producer warps.
 //   grid: (tiles over ext columns, splits over row chunks); each CTA writes one partial tile to
-//         Wp[split]; ymake/tinv sum the partials in a fixed order (deterministic).
-//   CTA : WM*WN consumer warps (32x32 warp tiles of 8x8x4 DMMAs) + 1 TMA producer warp.
+//         Wp[split]; k_wreduce sums the partials in a fixed order (deterministic).
+//   CTA : WM*WN consumer warps (32x32 warp tiles of 8x8x4 DMMAs) + NPW TMA producer warps, 2 stages.
 // ------------------------------------------------------------------------------------------------
 struct GemmVtaArgs {
-    const double* V;    // window row 0, first V column of this block
-    int64_t ldv;
-    int nv;             // leading ext columns taken from V itself (Gram block S = V'V); 0 or NBP
+    const double* vpk;  // packed V, window row 0
+    int voff;           // first packed column of this V block
+    int nv;             // leading ext columns taken from V itself (Gram block S = V'V); == NBP
     const double* A;    // window row 0, first trailing column
     int64_t lda;
     int64_t rows;       // valid rows of A in the window
     int na;             // trailing columns
-    int nchunks;        // ceil(rows / KC)
+    int nchunks;        // ceil(rows / KC1)
     int a_aligned;      // 1: every A column start is 16B aligned (bulk copies legal)
     double* Wp;         // partials: [split][next_pad][NBP]
     int64_t pstride;    // elements between consecutive partials
 };
 
-template <int NBP, int BN, int WM, int WN, int STAGES>
-__global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs a) {
+template <int NBP, int BN, int WM, int WN, int NPW>
+__global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) k_gemm_vta(GemmVtaArgs a) {
     constexpr int NCW = WM * WN;
+    constexpr int STAGES = 2;
     constexpr int WTM = NBP / WM, WTN = BN / WN;
     constexpr int MI = WTM / 8, NJ = WTN / 8;
-    static_assert(WTM % 8 == 0 && WTN % 8 == 0, "warp tile");
+    constexpr int CPW = BN / NPW;   // B columns per producer warp
+    static_assert(WTM % 8 == 0 && WTN % 8 == 0 && BN % NPW == 0, "tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][NBP][LDK]
-    double* sB = sV + STAGES * NBP * LDK;                // [STAGES][BN][LDK]
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BN * LDK);
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][NBP][LD1]
+    double* sB = sV + STAGES * NBP * LD1;                // [STAGES][BN][LD1]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BN * LD1);
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -127,50 +148,54 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs 
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], NPW);
             mbar_init(&empty[s], NCW);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        // ===== TMA producer warp =====
+    if (warp >= NCW) {
+        // ===== TMA producer warps =====
+        const int pw = warp - NCW;
+        const int cbeg = pw * CPW, cend = min(cbeg + CPW, ncols_tile);
         for (int it = 0; it < nit; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            const int64_t krow = (int64_t)(ch0 + it) * KC;
+            const int64_t q = ch0 + it;
+            const int64_t krow = q * KC1;
             const int64_t left = a.rows - krow;
-            const int nvalid = left >= KC ? KC : (int)left;          // valid A rows in this chunk (>= 1)
+            const int nvalid = left >= KC1 ? KC1 : (int)left;        // valid A rows in this chunk (>= 1)
             const int nbulk = a.a_aligned ? (nvalid & ~1) : 0;        // rows moved by TMA per A column
-            double* dV = sV + (size_t)s * NBP * LDK;
-            double* dB = sB + (size_t)s * BN * LDK;
+            double* dV = sV + (size_t)s * NBP * LD1;
+            double* dB = sB + (size_t)s * BN * LD1;
+            const double* vchunk = a.vpk + q * VPK_CHUNK;
             // generic-proxy fill of what TMA cannot move (ragged tail / unaligned user storage)
-            uint32_t bytes = NBP * KC * 8;
-            for (int c = lane; c < ncols_tile; c += 32) {
+            for (int c = cbeg + lane; c < cend; c += 32) {
                 const int jg = col0 + c;
-                if (jg >= a.nv && nbulk < KC) {
+                if (jg >= a.nv && nbulk < KC1) {
                     const double* src = a.A + (int64_t)(jg - a.nv) * a.lda + krow;
-                    double* dst = dB + c * LDK;
-                    for (int r = nbulk; r < KC; ++r) dst[r] = r < nvalid ? src[r] : 0.0;
+                    double* dst = dB + c * LD1;
+                    for (int r = nbulk; r < KC1; ++r) dst[r] = r < nvalid ? src[r] : 0.0;
                 }
             }
-            // every lane needs the byte total: count columns of each kind in this tile
-            {
-                const int nvcols = max(min(a.nv - col0, ncols_tile), 0);
-                bytes += (uint32_t)nvcols * KC * 8 + (uint32_t)(ncols_tile - nvcols) * nbulk * 8;
+            const int nvc = max(min(a.nv - col0, cend) - cbeg, 0);    // columns of this warp that come from V
+            const int nac = max(cend - cbeg, 0) - nvc;                // ... and from A
+            uint32_t bytes = (uint32_t)nvc * KC1 * 8 + (uint32_t)nac * nbulk * 8;
+            if (pw == 0) bytes += NBP * LD1 * 8;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], bytes);
+                if (pw == 0) bulk_g2s(dV, vchunk + (int64_t)a.voff * LD1, NBP * LD1 * 8, &full[s]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
-            __syncwarp();
-            for (int c = lane; c < NBP; c += 32) bulk_g2s(dV + c * LDK, a.V + (int64_t)c * a.ldv + krow, KC * 8, &full[s]);
-            for (int c = lane; c < ncols_tile; c += 32) {
+            for (int c = cbeg + lane; c < cend; c += 32) {
                 const int jg = col0 + c;
                 if (jg < a.nv) {
-                    bulk_g2s(dB + c * LDK, a.V + (int64_t)jg * a.ldv + krow, KC * 8, &full[s]);
+                    bulk_g2s(dB + c * LD1, vchunk + (int64_t)(a.voff + jg) * LD1, KC1 * 8, &full[s]);
                 } else if (nbulk > 0) {
-                    bulk_g2s(dB + c * LDK, a.A + (int64_t)(jg - a.nv) * a.lda + krow, nbulk * 8, &full[s]);
+                    bulk_g2s(dB + c * LD1, a.A + (int64_t)(jg - a.nv) * a.lda + krow, nbulk * 8, &full[s]);
                 }
             }
         }
@@ -185,21 +210,21 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int frag = (lane >> 2) * LDK + (lane & 3);
+    const int frag = (lane >> 2) * LD1 + (lane & 3);
     for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         release_prev_stage(empty, it, STAGES, lane);
-        const double* v = sV + (size_t)s * NBP * LDK + wm * WTM * LDK + frag;
-        const double* b = sB + (size_t)s * BN * LDK + wn * WTN * LDK + frag;
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
+        const double* v = sV + (size_t)s * NBP * LD1 + wm * WTM * LD1 + frag;
+        const double* b = sB + (size_t)s * BN * LD1 + wn * WTN * LD1 + frag;
+#pragma unroll 4
+        for (int kk = 0; kk < KC1 / 4; ++kk) {
             double af[MI], bf[NJ];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = v[i * 8 * LDK + kk * 4];
+            for (int i = 0; i < MI; ++i) af[i] = v[i * 8 * LD1 + kk * 4];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = b[j * 8 * LDK + kk * 4];
+            for (int j = 0; j < NJ; ++j) bf[j] = b[j * 8 * LD1 + kk * 4];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -219,11 +244,30 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) k_gemm_vta(GemmVtaArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
+// wreduce:  Ws[e] = sum_p Wp[p][e]   (fixed order -> deterministic), e over next*NBP elements
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wreduce(const double* __restrict__ Wp, int64_t pstride, int nsplit, int64_t nelem,
+                                                 double* __restrict__ Ws) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += (int64_t)gridDim.x * blockDim.x) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int p = 0;
+        for (; p + 4 <= nsplit; p += 4) {
+            s0 += Wp[(int64_t)p * pstride + e];
+            s1 += Wp[(int64_t)(p + 1) * pstride + e];
+            s2 += Wp[(int64_t)(p + 2) * pstride + e];
+            s3 += Wp[(int64_t)(p + 3) * pstride + e];
+        }
+        for (; p < nsplit; ++p) s0 += Wp[(int64_t)p * pstride + e];
+        Ws[e] = (s0 + s1) + (s2 + s3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gemm_cvy:  C(rows x ncols) += V(rows x nbp) * Y(nbp x ncols)   on rows >= row_lo   ("NN", K = nbp)
 //   Y already carries the minus sign and T' (ymake), so this is A_trail <- (I - V T' V') A_trail.
-//   grid: (row tiles of BM, column tiles of BN); 2 CTAs per SM so one CTA's C-tile load/store
-//   overlaps the other's MMA main loop.  CTA: WM*WN consumer warps (64x32 warp tiles) + 1 TMA warp.
-//   V and Y live in handle-owned, padded, 16B-aligned buffers -> every stage is pure TMA.
+//   grid: (row tiles of 128, column tiles of 64); 2 CTAs per SM so one CTA's C-tile load/store
+//   overlaps the other's MMA main loop.  CTA: 4 consumer warps (64x32 warp tiles) + 1 TMA warp.
+//   Every stage is three bulk copies: two 64x32 slices of vpk and one 32x64 block of ypk.
 // ------------------------------------------------------------------------------------------------
 struct GemmCvyArgs {
     double* C;          // window row 0, first column
@@ -231,29 +275,29 @@ struct GemmCvyArgs {
     int64_t rows;       // valid rows in the window
     int64_t row_lo;     // rows below this index (window-relative) are left untouched
     int ncols;
-    const double* V;    // window row 0; ldv multiple of BM, rows padded with zeros
-    int64_t ldv;
-    const double* Y;    // nbp x ncols_pad, ld = ldy
-    int64_t ldy;
-    int nbp;            // multiple of KC
+    const double* vpk;  // packed V, window row 0 (rows padded to a multiple of 128 with zeros)
+    int voff;           // first packed column of this V block
+    const double* ypk;  // packed Y: [n_tile][k_chunk][64][LDK]
+    int nkq;            // k-chunks (of KC columns) to run
+    int nkq_alloc;      // k-chunks per n_tile in ypk (tile stride)
 };
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
-__global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
-    constexpr int NCW = WM * WN;
-    constexpr int WTM = BM / WM, WTN = BN / WN;
+template <int MINB>
+__global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
+    constexpr int BM = 128, BN = YT, WN = 2, NCW = 4, STAGES = 2;
+    constexpr int WTM = 64, WTN = 32;
     constexpr int MI = WTM / 8, NJ = WTN / 8;
-    constexpr int LDV = BM + 4;   // (BM + 4) % 16 == 4 -> conflict-free A-fragment loads
+    constexpr int VH = KC * LD1;   // doubles per 64-row x 32-col slice
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][KC][LDV]
-    double* sY = sV + STAGES * KC * LDV;                 // [STAGES][BN][LDK]
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][2][KC][LD1]
+    double* sY = sV + STAGES * 2 * VH;                   // [STAGES][BN][LDK]
     uint64_t* full = reinterpret_cast<uint64_t*>(sY + STAGES * BN * LDK);
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
-    const int nit = a.nbp / KC;
+    const int nit = a.nkq;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -266,17 +310,19 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyAr
 
     if (warp == NCW) {
         // ===== TMA producer warp =====
-        for (int it = 0; it < nit; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(KC * BM * 8 + BN * KC * 8));
-            __syncwarp();
-            double* dV = sV + (size_t)s * KC * LDV;
-            double* dY = sY + (size_t)s * BN * LDK;
-            const int k0 = it * KC;
-            for (int c = lane; c < KC; c += 32) bulk_g2s(dV + c * LDV, a.V + (int64_t)(k0 + c) * a.ldv + m0, BM * 8, &full[s]);
-            for (int c = lane; c < BN; c += 32) bulk_g2s(dY + c * LDK, a.Y + (int64_t)(n0 + c) * a.ldy + k0, KC * 8, &full[s]);
+        if (lane == 0) {
+            const double* v0 = a.vpk + (int64_t)(2 * blockIdx.x) * VPK_CHUNK + (int64_t)a.voff * LD1;
+            const double* y0 = a.ypk + (int64_t)blockIdx.y * a.nkq_alloc * (BN * LDK);
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * VH + BN * LDK) * 8));
+                double* dV = sV + (size_t)s * 2 * VH;
+                bulk_g2s(dV, v0 + (int64_t)it * VH, VH * 8, &full[s]);
+                bulk_g2s(dV + VH, v0 + VPK_CHUNK + (int64_t)it * VH, VH * 8, &full[s]);
+                bulk_g2s(sY + (size_t)s * BN * LDK, y0 + (int64_t)it * (BN * LDK), BN * LDK * 8, &full[s]);
+            }
         }
         return;
     }
@@ -298,20 +344,20 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyAr
             acc[i][j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
         }
     }
-    const int fragA = (lane & 3) * LDV + (lane >> 2);
+    const int fragA = (lane & 3) * LD1 + (lane >> 2);
     const int fragB = (lane >> 2) * LDK + (lane & 3);
     for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         release_prev_stage(empty, it, STAGES, lane);
-        const double* v = sV + (size_t)s * KC * LDV + wm * WTM + fragA;
+        const double* v = sV + (size_t)s * 2 * VH + wm * VH + fragA;
         const double* y = sY + (size_t)s * BN * LDK + wn * WTN * LDK + fragB;
 #pragma unroll
         for (int kk = 0; kk < KC / 4; ++kk) {
             double af[MI], bf[NJ];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LDV + i * 8];
+            for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LD1 + i * 8];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) bf[j] = y[j * 8 * LDK + kk * 4];
 #pragma unroll
@@ -335,14 +381,13 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, MINB) k_gemm_cvy(GemmCvyAr
 }
 
 // ------------------------------------------------------------------------------------------------
-// tinv:  Linv = (I + stril(S))^{-1},  S = sum of the Gram partials (first NBP ext columns of Wp).
+// tinv:  Linv = (I + stril(S))^{-1},  S = first NBP ext columns of the reduced Wext.
 //   With |v|^2 = 2 the compact-WY factor obeys T^{-1} = I + striu(V'V), so Linv == T'.
 //   One CTA; 32x32 diagonal blocks by forward substitution, then two levels of
 //   X21 = -X22 (L21 X11).
 // ------------------------------------------------------------------------------------------------
 template <int NBP>
-__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Wp, int64_t pstride, int nsplit,
-                                                 double* __restrict__ Linv) {
+__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv) {
     constexpr int LDL = NBP + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
@@ -350,10 +395,7 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Wp, 
     const int tid = threadIdx.x;
     for (int e = tid; e < NBP * NBP; e += blockDim.x) {
         const int i = e % NBP, j = e / NBP;
-        double s = 0.0;
-        if (i > j)
-            for (int p = 0; p < nsplit; ++p) s += Wp[(int64_t)p * pstride + (int64_t)j * NBP + i];
-        L[j * LDL + i] = s;
+        L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
     }
     __syncthreads();
     // diagonal 32x32 blocks: X = (I + N)^{-1}; thread = one column of one block
@@ -378,25 +420,22 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Wp, 
     // merge levels
     for (int bs = 32; bs < NBP; bs *= 2) {
         const int npairs = NBP / (2 * bs);
-        for (int p = 0; p < npairs; ++p) {
-            const int o = p * 2 * bs;
-            // T = L21 * X11      (bs x bs), T(i,j) at j*bs + i   (bs*bs <= 4096 <= scratch)
-            for (int e = tid; e < bs * bs; e += blockDim.x) {
-                const int i = e % bs, j = e / bs;
-                double s = 0.0;
-                for (int k = j; k < bs; ++k) s += L[(o + k) * LDL + o + bs + i] * L[(o + j) * LDL + o + k];
-                T[j * bs + i] = s;
-            }
-            __syncthreads();
-            // X21 = -X22 * T
-            for (int e = tid; e < bs * bs; e += blockDim.x) {
-                const int i = e % bs, j = e / bs;
-                double s = 0.0;
-                for (int k = 0; k <= i; ++k) s += L[(o + bs + k) * LDL + o + bs + i] * T[j * bs + k];
-                L[(o + j) * LDL + o + bs + i] = -s;
-            }
-            __syncthreads();
+        // T_p = L21 * X11 for every pair p      (bs x bs each; npairs * bs * bs <= 4096 <= scratch)
+        for (int e = tid; e < npairs * bs * bs; e += blockDim.x) {
+            const int p = e / (bs * bs), r = e % (bs * bs), i = r % bs, j = r / bs, o = p * 2 * bs;
+            double s = 0.0;
+            for (int k = j; k < bs; ++k) s += L[(o + k) * LDL + o + bs + i] * L[(o + j) * LDL + o + k];
+            T[p * bs * bs + j * bs + i] = s;
         }
+        __syncthreads();
+        // X21 = -X22 * T_p
+        for (int e = tid; e < npairs * bs * bs; e += blockDim.x) {
+            const int p = e / (bs * bs), r = e % (bs * bs), i = r % bs, j = r / bs, o = p * 2 * bs;
+            double s = 0.0;
+            for (int k = 0; k <= i; ++k) s += L[(o + bs + k) * LDL + o + bs + i] * T[p * bs * bs + j * bs + k];
+            L[(o + j) * LDL + o + bs + i] = -s;
+        }
+        __syncthreads();
     }
     for (int e = tid; e < NBP * NBP; e += blockDim.x) {
         const int i = e % NBP, j = e / NBP;
@@ -405,14 +444,14 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Wp, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// ymake:  Y(NBP x na) = -Linv * (sum of W partials)     (W = ext columns [nv, nv+na))
-//   CTA = YCOLS columns; thread = (row i, half of the columns).
+// ymake:  Y(NBP x na) = -Linv * W   (W = ext columns [NBP, NBP+na) of the reduced Wext), written in
+//   the packed layout gemm_cvy stages with one bulk copy:  ypk[col/64][k/32][col%64][LDK].
+//   CTA = YCOLS columns; thread = (row i, a group of the columns).
 // ------------------------------------------------------------------------------------------------
 constexpr int YCOLS = 32;
 template <int NBP>
-__global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Wp, int64_t pstride, int nsplit, int nv,
-                                                  int na, const double* __restrict__ Linv, double* __restrict__ Y,
-                                                  int64_t ldy) {
+__global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int na, const double* __restrict__ Linv,
+                                                  double* __restrict__ ypk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sL = reinterpret_cast<double*>(smem_raw);   // [NBP][NBP] col-major
     double* sW = sL + NBP * NBP;                         // [YCOLS][NBP]
@@ -421,28 +460,26 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Wp,
     const int nc = min(YCOLS, na - c0);
     for (int e = tid; e < NBP * NBP; e += blockDim.x) sL[e] = Linv[e];
     for (int e = tid; e < YCOLS * NBP; e += blockDim.x) {
-        const int k = e % NBP, j = e / NBP;
-        double s = 0.0;
-        if (j < nc)
-            for (int p = 0; p < nsplit; ++p) s += Wp[(int64_t)p * pstride + (int64_t)(nv + c0 + j) * NBP + k];
-        sW[e] = s;
+        const int j = e / NBP;
+        sW[e] = (j < nc) ? Ws[(int64_t)(NBP + c0) * NBP + e] : 0.0;
     }
     __syncthreads();
     constexpr int TPR = 256 / NBP;           // threads per row (2 for 128, 8 for 32)
     constexpr int CPT = YCOLS / TPR;         // columns per thread
+    constexpr int NKQ = NBP / KC;
     const int i = tid % NBP, jh = tid / NBP;
     double acc[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[j] = 0.0;
-    for (int k = 0; k < NBP; ++k) {
+    for (int k = 0; k <= i; ++k) {            // Linv is lower triangular
         const double l = sL[k * NBP + i];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) acc[j] += l * sW[(jh * CPT + j) * NBP + k];
     }
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        const int col = c0 + jh * CPT + j;
-        if (col < na) Y[(int64_t)col * ldy + i] = -acc[j];
+        const int col = c0 + jh * CPT + j;     // columns beyond na get zeros (the tile is copied whole)
+        ypk[((int64_t)(col / YT) * NKQ + i / KC) * (YT * LDK) + (col % YT) * LDK + (i % KC)] = (col < na) ? -acc[j] : 0.0;
     }
 }
 
@@ -450,10 +487,13 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Wp,
 // panel:  cooperative, persistent factorisation of an mp x ncols (ncols <= IB) panel.
 //   Each CTA keeps a slab of rows in shared memory for the whole kernel.  One grid-wide
 //   reduction per column: the same pass that applies reflector j also accumulates
-//   x'a_c (x = next pivot column, rows > j) for every remaining column c, so that after the barrier
+//   x'a_c (x = next pivot column, rows > j) for every remaining column c, so that after the exchange
 //   every CTA can form   s=|x|, alpha, f   and   w_c = v'a_c = f (x'a_c - alpha a_c[j])   locally
-//   (S:129-131 and S:208 in one reduction).  Partials are summed in CTA order (deterministic).
-//   Also writes the packed V block (zero above the diagonal, zero padding rows) for the GEMMs.
+//   (S:129-131 and S:208 in one reduction).
+//   The exchange is all-to-all through L2 with self-validating cells (the NCCL "LL" idea): each
+//   8-byte word carries 32 data bits and a 32-bit tag unique to (launch, column), so a reader needs
+//   no fence, no atomic and no barrier — one L2 round trip per column.  Partials are summed in CTA
+//   order (deterministic).  Also writes the packed V block (vpk) for the GEMMs.
 // ------------------------------------------------------------------------------------------------
 struct PanelArgs {
     double* P;            // panel top-left (row = pivot row of column 0)
@@ -461,31 +501,31 @@ struct PanelArgs {
     int64_t mp;           // rows
     int ncols;            // active columns (<= IB)
     double* alpha;        // alpha[0:ncols]
-    double* Vout;         // V block column 0 of this sub-panel, window row 0 (may be null)
-    int64_t ldv;
-    int64_t vtop;         // window rows above the panel top (zero-filled in Vout)
+    double* vpk;          // packed V of the outer panel (may be null)
+    int voff;             // first packed column of this sub-panel
+    int64_t vtop;         // window rows above the panel top (zero-filled in vpk)
     int64_t vrows;        // total window rows incl. padding (zero-filled below vtop+mp)
     int rows_per_cta;
     int lds;              // slab leading dimension (>= rows_per_cta, odd)
-    double* part;         // [2][gridDim.x][IB]
-    double* piv;          // [2][IB]
-    unsigned long long* bar;
-    unsigned long long bar_base;   // barrier counter value at launch
+    unsigned long long* cells;   // [IB+1 steps][gridDim.x+1][IB][2]
+    uint32_t epoch;       // tags epoch+1 .. epoch+IB+1 belong to this launch
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1ULL);
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-        } while (v < target);
-        __threadfence();
-    }
-    __syncthreads();
+__device__ __forceinline__ void ll_store(unsigned long long* cell, double v, uint32_t tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
 }
+__device__ __forceinline__ void ll_peek(const unsigned long long* cell, unsigned long long& w0, unsigned long long& w1) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(cell) : "memory");
+}
+__device__ __forceinline__ double ll_finish(const unsigned long long* cell, unsigned long long w0, unsigned long long w1, uint32_t tag) {
+    while ((uint32_t)(w0 >> 32) != tag || (uint32_t)(w1 >> 32) != tag) ll_peek(cell, w0, w1);
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
+constexpr int PANEL_MAXG = 160;                       // max CTAs of the panel kernel
+constexpr int PANEL_GPW = PANEL_MAXG / (PANEL_THREADS / 32);   // cells gathered per thread (20)
 
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -500,32 +540,52 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     const int64_t row0 = (int64_t)cta * a.rows_per_cta;
     const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - row0));
     const int lds = a.lds, nc = a.ncols;
+    const size_t step_stride = (size_t)(G + 1) * IB * 2;   // u64 words per step
+    auto cell = [&](int step, int g, int c) { return a.cells + (size_t)step * step_stride + ((size_t)g * IB + c) * 2; };
 
     // load slab (coalesced along rows)
     for (int c = warp; c < nc; c += NW)
         for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
     __syncthreads();
 
-    // partial dots of column 0 against every column (all rows), and the pivot row
+    // step 0: partial dots of column 0 against every column (all rows), and the pivot row
     for (int c = warp; c < nc; c += NW) {
         double acc = 0.0;
         for (int r = lane; r < nr; r += 32) acc += S[r] * S[c * lds + r];
         acc = warp_sum(acc);
-        if (lane == 0) a.part[((size_t)0 * G + cta) * IB + c] = acc;
+        if (lane == 0) ll_store(cell(0, cta, c), acc, a.epoch + 1);
     }
-    if (cta == 0 && tid < nc) a.piv[tid] = S[tid * lds + 0];
+    if (cta == 0 && tid < nc) ll_store(cell(0, G, tid), S[tid * lds + 0], a.epoch + 1);
 
-    unsigned long long target = a.bar_base;
     for (int j = 0; j < nc; ++j) {
-        target += G;
-        grid_barrier(a.bar, target);
-        const int buf = j & 1;
-        // deterministic reduction of the partials: thread (q = warp, c = lane) sums CTAs q, q+NW, ...
+        const uint32_t tag = a.epoch + 1 + j;
+        // gather: thread (q = warp, c = lane) sums the cells of CTAs q, q+NW, ... in that order.
+        // All loads are issued before any tag is checked -> one L2 round trip when everyone is on time.
         {
             double acc = 0.0;
-            if (lane >= j && lane < nc)
-                for (int g = warp; g < G; g += NW) acc += __ldcg(&a.part[((size_t)buf * G + g) * IB + lane]);
+            if (lane >= j && lane < nc) {
+                unsigned long long w0[PANEL_GPW], w1[PANEL_GPW];
+#pragma unroll
+                for (int t = 0; t < PANEL_GPW; ++t) {
+                    const int g = warp + t * NW;
+                    if (g < G) ll_peek(cell(j, g, lane), w0[t], w1[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < PANEL_GPW; ++t) {
+                    const int g = warp + t * NW;
+                    if (g < G) acc += ll_finish(cell(j, g, lane), w0[t], w1[t], tag);
+                }
+            }
             red[warp][lane] = acc;
+            if (warp == NW - 1) {
+                double p = 0.0;
+                if (lane >= j && lane < nc) {
+                    unsigned long long x0, x1;
+                    ll_peek(cell(j, G, lane), x0, x1);
+                    p = ll_finish(cell(j, G, lane), x0, x1, tag);
+                }
+                pv[lane] = p;
+            }
         }
         __syncthreads();
         if (tid < IB) {
@@ -533,7 +593,6 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
 #pragma unroll
             for (int q = 0; q < NW; ++q) s += red[q][tid];
             tot[tid] = s;
-            pv[tid] = (tid >= j && tid < nc) ? __ldcg(&a.piv[buf * IB + tid]) : 0.0;
         }
         __syncthreads();
         // S:129-131
@@ -548,21 +607,20 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         const int r_lo = rj < 0 ? 0 : (rj > nr ? nr : (int)rj);   // first active local row
         // step 1: v = f (x - alpha e_j) in place; next pivot column updated in place
         const bool has_next = j + 1 < nc;
-        const double w1 = has_next ? f * (tot[j + 1] - alpha * pv[j + 1]) : 0.0;
+        const double w1n = has_next ? f * (tot[j + 1] - alpha * pv[j + 1]) : 0.0;
         for (int r = r_lo + tid; r < nr; r += PANEL_THREADS) {
             double x = S[j * lds + r];
             if (row0 + r == j) x -= alpha;
             const double v = f * x;
             S[j * lds + r] = v;
-            if (has_next) S[(j + 1) * lds + r] -= v * w1;
+            if (has_next) S[(j + 1) * lds + r] -= v * w1n;
         }
         __syncthreads();
         if (has_next) {
-            const int nbuf = buf ^ 1;
             // rows that enter the next column's dots: global row >= j+1
             const int64_t rj1 = (int64_t)j + 1 - row0;
             const int r_lo1 = rj1 < 0 ? 0 : (rj1 > nr ? nr : (int)rj1);
-            // step 2: tasks t = j+1 .. nc-1; t == j+1 is the self-dot, others update + dot
+            // step 2: tasks c = j+1 .. nc-1; c == j+1 is the self-dot, others update + dot
             for (int c = j + 1 + warp; c < nc; c += NW) {
                 double acc = 0.0;
                 if (c == j + 1) {
@@ -579,11 +637,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                     }
                 }
                 acc = warp_sum(acc);
-                if (lane == 0) a.part[((size_t)nbuf * G + cta) * IB + c] = acc;
+                if (lane == 0) ll_store(cell(j + 1, cta, c), acc, tag + 1);
             }
             if (cta == 0) {
                 __syncthreads();
-                if (tid > j && tid < nc) a.piv[nbuf * IB + tid] = S[tid * lds + (j + 1)];
+                if (tid > j && tid < nc) ll_store(cell(j + 1, G, tid), S[tid * lds + (j + 1)], tag + 1);
             }
         }
     }
@@ -591,32 +649,40 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     // write back the factored slab, and the packed V block
     for (int c = warp; c < nc; c += NW)
         for (int r = lane; r < nr; r += 32) a.P[(int64_t)c * a.ldp + row0 + r] = S[c * lds + r];
-    if (a.Vout) {
+    if (a.vpk) {
         for (int c = warp; c < IB; c += NW) {
-            double* vc = a.Vout + (int64_t)c * a.ldv;
-            for (int r = lane; r < nr; r += 32) vc[a.vtop + row0 + r] = (c < nc && row0 + r >= c) ? S[c * lds + r] : 0.0;
+            const int pc = a.voff + c;
+            for (int r = lane; r < nr; r += 32)
+                a.vpk[vpk_index(a.vtop + row0 + r, pc)] = (c < nc && row0 + r >= c) ? S[c * lds + r] : 0.0;
             if (cta == 0)
-                for (int64_t r = lane; r < a.vtop; r += 32) vc[r] = 0.0;
+                for (int64_t r = lane; r < a.vtop; r += 32) a.vpk[vpk_index(r, pc)] = 0.0;
             if (cta == G - 1)
-                for (int64_t r = a.vtop + a.mp + lane; r < a.vrows; r += 32) vc[r] = 0.0;
+                for (int64_t r = a.vtop + a.mp + lane; r < a.vrows; r += 32) a.vpk[vpk_index(r, pc)] = 0.0;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// pack_v: copy the Householder block stored in place in A (lower trapezoid incl. diagonal) into the
-// packed V buffer for the solve phase (S:232-242 reads H in place; the GEMM path wants zeros above).
+// pack: copy a Householder block into the packed V layout (vpk).  tril != 0: the block is stored in
+// place in A (lower trapezoid incl. diagonal, S:232-242 reads H in place; the GEMM path wants zeros
+// above the diagonal); tril == 0: plain copy (kernel-level test hook).  Columns >= kb and rows
+// outside [vtop, vtop+mp) are zero-filled.  grid.y = packed columns to write.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_v(const double* __restrict__ A, int64_t lda, int64_t mp, int kb, double* __restrict__ V,
-                         int64_t ldv, int64_t vtop, int64_t vrows, int nbp) {
+__global__ void k_pack(const double* __restrict__ A, int64_t lda, int64_t mp, int kb, int tril, double* __restrict__ vpk,
+                       int voff, int64_t vtop, int64_t vrows) {
     const int c = blockIdx.y;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < vrows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pr = r - vtop;   // panel-relative row
         double v = 0.0;
-        if (c < kb && pr >= c && pr < mp) v = A[(int64_t)c * lda + pr];
-        V[(int64_t)c * ldv + r] = v;
+        if (c < kb && pr >= (tril ? c : 0) && pr < mp) v = A[(int64_t)c * lda + pr];
+        vpk[vpk_index(r, voff + c)] = v;
     }
-    (void)nbp;
+}
+// zero packed columns [c0, c1) over all chunks
+__global__ void k_vpk_zero_cols(double* __restrict__ vpk, int64_t nchunks, int c0, int c1) {
+    const int64_t per = (int64_t)(c1 - c0) * LD1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nchunks * per; e += (int64_t)gridDim.x * blockDim.x)
+        vpk[(e / per) * VPK_CHUNK + (int64_t)c0 * LD1 + e % per] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

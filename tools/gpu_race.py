@@ -15,14 +15,14 @@ def experiment(rows, nbp, ncols, iters):
     V = D.to_colmajor(np.tril(Hp), dev)
     C0 = D.colmajor_empty(rows, ncols, dev); D.fill_uniform_(C0, 5)
     nw = min(64 * 1024 * 1024 // 8, 3 * 148 * 128 * 128)
-    ny = 128 * (ncols + 128)
+    ny = 4 * 64 * 36 * ((ncols + 63) // 64)
     ref = None; bad = 0
     for it in range(iters):
         Cw = C0.clone() if False else D.colmajor_empty(rows, ncols, dev); Cw.copy_(C0)
         D._lib.call("dhqr_k_block_reflector_f64", h.raw, rows, nbp, vp(V), rows, 0, ncols, vp(Cw), rows, None, sp())
         W = torch.empty(nw, dtype=torch.float64, device=dev); Y = torch.empty(ny, dtype=torch.float64, device=dev); L = torch.empty(128 * 128, dtype=torch.float64, device=dev)
         D._lib.call("dhqr_debug_copy_f64", h.raw, b"wpart", vp(W), nw, sp())
-        D._lib.call("dhqr_debug_copy_f64", h.raw, b"ybuf", vp(Y), ny, sp())
+        D._lib.call("dhqr_debug_copy_f64", h.raw, b"ypk", vp(Y), ny, sp())
         D._lib.call("dhqr_debug_copy_f64", h.raw, b"linv", vp(L), 128 * 128, sp())
         torch.cuda.synchronize()
         if ref is None:
