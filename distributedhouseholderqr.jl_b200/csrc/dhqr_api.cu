@@ -101,23 +101,39 @@ struct dhqr_context {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     // options
-    int nb = 128, panel_ctas = 0, sync = 0;
+    int nb = 128, panel_ctas = 0, sync = 0, panel_backoff = 0, vta_max_chunks = 0;
     // workspace
-    double* vpk = nullptr;   size_t vpk_elems = 0;   int64_t vrows_cap = 0;   // packed V block [chunk][128][68]
-    double* wpart = nullptr; size_t wpart_elems = 0;                    // gemm_vta partials
-    double* wsum = nullptr;  size_t wsum_elems = 0;                     // reduced Wext
-    double* ypk = nullptr;   size_t ypk_elems = 0;                      // packed Y = -T'W
-    double* linv = nullptr;                                             // [128*128]
+    // two V buffers (panel k and panel k+1 live at the same time under look-ahead) and two workspace
+    // sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
+    double* vpk2[3] = {nullptr, nullptr, nullptr}; size_t vpk_elems[3] = {0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]
+    struct WSet {
+        double* wpart = nullptr; size_t wpart_elems = 0;                // gemm_vta partials
+        double* wsum = nullptr;  size_t wsum_elems = 0;                 // reduced Wext
+        double* ypk = nullptr;   size_t ypk_elems = 0;                  // packed Y = -T'W
+        double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
+    } ws[2];
+    cudaStream_t hp_stream = nullptr;                                   // high-priority stream of the panel chain
+    int lookahead = 1;
+    int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
+    std::vector<float> la_times;                                        // [k][3]: panel k done (hp), next k signalled (st), bulk k done (st), ms since start
     unsigned long long* cells = nullptr;                                // panel exchange cells [IB+1][MAXG+1][IB][2]
     uint32_t ll_epoch = 0;
+    unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
+    int cvy_stagger = 1;
+    long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
     double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
     double* hostB = nullptr; size_t hostB_elems = 0;
     int64_t* d_i64 = nullptr;                                           // small int64 scratch (partition exchange)
     int64_t launches = 0;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // compute stream of the _host_ entry points
+    cudaStream_t d2h_stream = nullptr;       // drains finished panels to the host while the factorisation continues
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> panel_events;
+    // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
+    double* mirror_host = nullptr;
+    int64_t mirror_lda = 0;
     // kernel attribute state
     bool attrs_set = false;
     // per-kernel-class CUDA-event profiling (option "profile")
@@ -174,21 +190,26 @@ static int ensure(T** p, size_t* have, size_t need) {
     return 0;
 }
 
+static constexpr int64_t WPART_TILES = 2304;   // capacity of the partial buffer in 128 x 64 tiles (151 MB per set)
+
 static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
     TRY(set_attrs(c));
     const int64_t vrows = rup(m, 128) + 128;
-    if (c->vrows_cap < vrows || !c->vpk) {
-        TRY(ensure(&c->vpk, &c->vpk_elems, (size_t)(vrows / KC1) * VPK_CHUNK));
+    if (c->vrows_cap < vrows || !c->vpk2[0]) {
+        for (int b = 0; b < 3; ++b) TRY(ensure(&c->vpk2[b], &c->vpk_elems[b], (size_t)(vrows / KC1) * VPK_CHUNK));
         c->vrows_cap = vrows;
     }
-    const int64_t maxctas = (int64_t)MAXCTAS_FACTOR * c->sms;
     const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
-    TRY(ensure(&c->wpart, &c->wpart_elems, (size_t)std::max(maxctas, tiles_max) * NBMAX * G1S_BN + (size_t)NBMAX * G1S_BN));
-    TRY(ensure(&c->wsum, &c->wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
-    TRY(ensure(&c->ypk, &c->ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
+    for (int b = 0; b < 2; ++b) {
+        auto& w = c->ws[b];
+        TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)std::max(WPART_TILES, tiles_max) * NBMAX * G1_BN));
+        TRY(ensure(&w.wsum, &w.wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
+        TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
+        TRY(ensure(&w.linv, &w.linv_elems, (size_t)NBMAX * NBMAX));
+    }
     size_t one = 0;
-    if (!c->linv) { one = 0; TRY(ensure(&c->linv, &one, (size_t)NBMAX * NBMAX)); }
-    if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)(IB + 1) * (PANEL_MAXG + 1) * IB * 2)); c->ll_epoch = 0; }
+    if (!c->sm_ticket) { CU(cudaMalloc((void**)&c->sm_ticket, sizeof(unsigned int) * 1024)); CU(cudaMemset(c->sm_ticket, 0, sizeof(unsigned int) * 1024)); }
+    if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)IB * (PANEL_MAXG + 2) * IB * 2)); c->ll_epoch = 0; }
     TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
     return 0;
@@ -233,11 +254,19 @@ static int post(dhqr_context* c, cudaStream_t st, const char* what, double work 
 // block-reflector application  C <- (I - V T' V') C  on window rows >= row_lo
 //   V: nbp columns of the packed V buffer starting at Vcols (window row 0), T from the Gram matrix.
 // ------------------------------------------------------------------------------------------------
-static int pick_splits(int tiles, int nchunks, int sms) {
-    int smax = std::max(1, std::min(nchunks / 4, (MAXCTAS_FACTOR * sms) / std::max(tiles, 1)));
-    int best = 1;
+// splits over the row chunks: fill whole waves of SMs; `max_chunks` (> 0) caps the chunks one CTA runs
+// through (look-ahead wants short-lived CTAs so that the high-priority panel chain gets SMs quickly)
+static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t cap_tiles) {
+    tiles = std::max(tiles, 1);
+    int smin = 1;
+    if (max_chunks > 0) smin = std::max(1, (nchunks + max_chunks - 1) / max_chunks);
+    int smax = std::max(1, std::min(nchunks / 4, (MAXCTAS_FACTOR * sms) / tiles));
+    smax = std::max(smax, std::min(smin + (sms + tiles - 1) / tiles, std::max(1, nchunks / 2)));
+    smax = (int)std::min<int64_t>(smax, std::max<int64_t>(1, cap_tiles / tiles));
+    smin = std::min(smin, smax);
+    int best = smin;
     double beste = 0.0;
-    for (int s = 1; s <= smax; ++s) {
+    for (int s = smin; s <= smax; ++s) {
         const int ctas = tiles * s;
         const double e = (double)ctas / ((double)sms * ((ctas + sms - 1) / sms));
         if (e > beste + 1e-9) { beste = e; best = s; }
@@ -245,25 +274,30 @@ static int pick_splits(int tiles, int nchunks, int sms) {
     return best;
 }
 
-static int apply_block_reflector(dhqr_context* c, cudaStream_t st, int voff, int nbp, int64_t rows, int64_t row_lo,
-                                 double* C, int64_t ldc, int ncols) {
-    // V = packed columns [voff, voff + nbp) of c->vpk (columns beyond the live ones are zero)
+// block-reflector application  C <- (I - V T' V') C  on window rows >= row_lo
+//   V = packed columns [voff, voff + nbp) of `vpk` (columns beyond the live ones are zero); T from the
+//   Gram matrix; `w` = the workspace set of the calling chain.
+static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int voff, int nbp,
+                                 int64_t rows, int64_t row_lo, double* C, int64_t ldc, int ncols, int max_chunks = 0,
+                                 bool reuse_T = false) {
+    // reuse_T: w.linv already holds T' of this V (same chain, previous call) -> skip the Gram block and k_tinv
     if (ncols <= 0 || rows <= 0) return 0;
     const bool small = (nbp <= 32);
     const int NBPK = small ? 32 : 128;          // kernel instantiation
     const int bn = small ? G1S_BN : G1_BN;
-    const int next = NBPK + ncols;
+    const int nv = reuse_T ? 0 : NBPK;
+    const int next = nv + ncols;
     const int tiles = (next + bn - 1) / bn;
     const int nchunks = (int)((rows + KC1 - 1) / KC1);
-    const int nsplit = pick_splits(tiles, nchunks, c->sms);
+    const int nsplit = pick_splits(tiles, nchunks, c->sms, max_chunks, (int64_t)(w.wpart_elems / ((size_t)bn * NBPK)));
     const int64_t pstride = (int64_t)tiles * bn * NBPK;
-    if ((size_t)(pstride * nsplit) > c->wpart_elems) return set_err(4001, "internal: W partial workspace too small");
-    if ((size_t)next * NBPK > c->wsum_elems) return set_err(4003, "internal: W workspace too small");
+    if ((size_t)(pstride * nsplit) > w.wpart_elems) return set_err(4001, "internal: W partial workspace too small");
+    if ((size_t)next * NBPK > w.wsum_elems) return set_err(4003, "internal: W workspace too small");
     GemmVtaArgs g1;
-    g1.vpk = c->vpk; g1.voff = voff; g1.nv = NBPK;
+    g1.vpk = vpk; g1.voff = voff; g1.nv = nv;
     g1.A = C; g1.lda = ldc; g1.rows = rows; g1.na = ncols; g1.nchunks = nchunks;
     g1.a_aligned = (((uintptr_t)C & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
-    g1.Wp = c->wpart; g1.pstride = pstride;
+    g1.Wp = w.wpart; g1.pstride = pstride;
     dim3 grid1(tiles, nsplit);
     pre(c, st);
     if (small) {
@@ -271,25 +305,28 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, int voff, int
     } else {
         K_G1_128<<<grid1, (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
     }
-    TRY(post(c, st, small ? "k_gemm_vta32" : "k_gemm_vta128", 2.0 * (double)rows * nbp * ((double)ncols + nbp)));
+    TRY(post(c, st, small ? "k_gemm_vta32" : "k_gemm_vta128", 2.0 * (double)rows * nbp * ((double)ncols + nv)));
     pre(c, st);
     const int64_t nelem = (int64_t)next * NBPK;
-    k_wreduce<<<(unsigned)std::min<int64_t>((nelem + 255) / 256, 8 * c->sms), 256, 0, st>>>(c->wpart, pstride, nsplit, nelem, c->wsum);
+    k_wreduce<<<(unsigned)std::min<int64_t>((nelem + 255) / 256, 8 * c->sms), 256, 0, st>>>(w.wpart, pstride, nsplit, nelem, w.wsum);
     TRY(post(c, st, "k_wreduce"));
-    pre(c, st);
-    if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(c->wsum, c->linv);
-    else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(c->wsum, c->linv);
-    TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
+    if (!reuse_T) {
+        pre(c, st);
+        if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(w.wsum, w.linv);
+        else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(w.wsum, w.linv);
+        TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
+    }
     pre(c, st);
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
-    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(c->wsum, ncols, c->linv, c->ypk);
-    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(c->wsum, ncols, c->linv, c->ypk);
+    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
+    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
     TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
     pre(c, st);
     GemmCvyArgs g2;
     g2.C = C; g2.ldc = ldc; g2.rows = rows; g2.row_lo = row_lo; g2.ncols = ncols;
-    g2.vpk = c->vpk; g2.voff = voff; g2.ypk = c->ypk;
+    g2.vpk = vpk; g2.voff = voff; g2.ypk = w.ypk;
     g2.nkq = small ? 1 : (int)(rup(nbp, KC) / KC); g2.nkq_alloc = NBPK / KC;
+    g2.sm_ticket = c->cvy_stagger ? c->sm_ticket : nullptr; g2.first_wave = 2 * c->sms; g2.stagger_cycles = 5200 * g2.nkq;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
     K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
     TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
@@ -299,9 +336,9 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, int voff, int
 // ------------------------------------------------------------------------------------------------
 // cooperative panel launch: factor mp x ncols (<= IB) at P, V block -> vout columns
 // ------------------------------------------------------------------------------------------------
-static int launch_panel(dhqr_context* c, cudaStream_t st, double* P, int64_t ldp, int64_t mp, int ncols, double* alpha,
-                        int voff, int64_t vtop, int64_t vrows, bool write_v = true) {
-    int gmax = c->panel_ctas > 0 ? c->panel_ctas : 96;
+static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P, int64_t ldp, int64_t mp, int ncols,
+                        double* alpha, int voff, int64_t vtop, int64_t vrows) {
+    int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->nranks == 1 && c->lookahead ? 64 : c->sms);
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
@@ -314,19 +351,19 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* P, int64_t ldp
     const size_t smem = (size_t)IB * lds * 8;
     if (smem > 200 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
     if (c->ll_epoch > 0xF0000000u) {   // tag space nearly used up: start over with clean cells
-        CU(cudaMemsetAsync(c->cells, 0, sizeof(unsigned long long) * (size_t)(IB + 1) * (PANEL_MAXG + 1) * IB * 2, st));
+        CU(cudaMemsetAsync(c->cells, 0, sizeof(unsigned long long) * (size_t)IB * (PANEL_MAXG + 2) * IB * 2, st));
         c->ll_epoch = 0;
     }
     PanelArgs a;
     a.P = P; a.ldp = ldp; a.mp = mp; a.ncols = ncols; a.alpha = alpha;
-    a.vpk = write_v ? c->vpk : nullptr; a.voff = voff; a.vtop = vtop; a.vrows = vrows;
+    a.vpk = vpk; a.voff = voff; a.vtop = vtop; a.vrows = vrows;
     a.rows_per_cta = (int)rpc; a.lds = lds;
-    a.cells = c->cells; a.epoch = c->ll_epoch;
+    a.cells = c->cells; a.epoch = c->ll_epoch; a.trace = c->panel_trace; a.backoff = c->panel_backoff;
     void* args[] = {&a};
     pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
     if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_panel failed: %s", cudaGetErrorString(e));
-    c->ll_epoch += IB + 1;
+    c->ll_epoch += IB;
     return post(c, st, "k_panel", 16.0 * (double)mp * ncols);   // work = bytes: panel read once + written once
 }
 
@@ -381,6 +418,155 @@ static int check_common(dhqr_context* c, int64_t m, int64_t n_global, int64_t co
 // ------------------------------------------------------------------------------------------------
 // qr!: blocked driver  (S:113-148, S:198-213)
 // ------------------------------------------------------------------------------------------------
+struct PanelGeom { int64_t r0, rows, vrows; int nbp; };
+static PanelGeom panel_geom(const Panel& p, int64_t m) {
+    PanelGeom g;
+    g.r0 = p.c & ~(int64_t)31;              // window start: 32-row aligned for the TMA chunks
+    g.rows = m - g.r0;                       // valid window rows
+    g.vrows = rup(g.rows, 128);
+    g.nbp = (int)rup(p.kb, IB);
+    return g;
+}
+
+// factor one outer panel on stream st: inner panels of IB columns + updates inside the outer panel; V -> vpk
+static int factor_outer_panel(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
+                              int64_t col0, double* A, int64_t lda, double* alpha) {
+    const PanelGeom g = panel_geom(p, m);
+    for (int o = 0; o < p.kb; o += IB) {
+        const int ib = std::min(IB, p.kb - o);
+        const int64_t cs = p.c + o;                                   // global column == pivot row
+        double* P = A + (cs - col0) * lda + cs;
+        TRY(launch_panel(c, st, vpk, P, lda, m - cs, ib, alpha + cs, o, cs - g.r0, g.vrows));
+        const int rem = p.kb - (o + ib);
+        if (rem > 0)   // update the rest of the outer panel with this sub-panel's reflectors
+            TRY(apply_block_reflector(c, st, vpk, w, o, IB, g.rows, cs - g.r0, A + (cs + ib - col0) * lda + g.r0, lda, rem));
+    }
+    if (g.nbp > IB && g.nbp < NBMAX) {   // zero the V columns the 128-wide kernels read beyond nbp
+        k_vpk_zero_cols<<<2 * c->sms, 256, 0, st>>>(vpk, g.vrows / KC1, g.nbp, NBMAX);
+        TRY(post(c, st, "k_vpk_zero_cols"));
+    }
+    return 0;
+}
+
+static int mirror_panel_to_host(dhqr_context* c, cudaStream_t st, const Panel& p, int64_t m, int64_t col0, const double* A,
+                                int64_t lda) {
+    if (!c->mirror_host) return 0;   // host entry point only: this panel's columns are final -> start their D2H now
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->panel_events.push_back(ev);
+    CU(cudaEventRecord(ev, st));
+    CU(cudaStreamWaitEvent(c->d2h_stream, ev, 0));
+    CU(cudaMemcpy2DAsync(c->mirror_host + p.c * c->mirror_lda, (size_t)c->mirror_lda * 8, A + (p.c - col0) * lda, (size_t)lda * 8,
+                         (size_t)m * 8, (size_t)p.kb, cudaMemcpyDeviceToHost, c->d2h_stream));
+    return 0;
+}
+
+// single stream, one panel after the other (multi-GPU path; also option lookahead = 0)
+static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
+                             double* alpha, const std::vector<Panel>& panels) {
+    const int64_t lend = col0 + nl;
+    double* vpk = c->vpk2[0];
+    auto& w = c->ws[0];
+    for (const Panel& p : panels) {
+        const PanelGeom g = panel_geom(p, m);
+        if (c->rank == p.owner) {
+            TRY(factor_outer_panel(c, st, vpk, w, p, m, col0, A, lda, alpha));
+            TRY(mirror_panel_to_host(c, st, p, m, col0, A, lda));
+        }
+        if (c->nranks > 1) {
+            // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
+            NC(g_nccl.Broadcast(vpk, vpk, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, p.owner, c->comm, st));
+            NC(g_nccl.Broadcast(alpha + p.c, alpha + p.c, (size_t)p.kb, ncclFloat64, p.owner, c->comm, st));
+        }
+        // trailing update of the local columns right of the panel (S:198-213 for nb columns at once)
+        const int64_t t0 = std::max(p.c + p.kb, col0);
+        if (t0 < lend)
+            TRY(apply_block_reflector(c, st, vpk, w, 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda, (int)(lend - t0)));
+    }
+    return 0;
+}
+
+// look-ahead (single GPU): the panel chain (latency bound: one grid-wide exchange per column) runs on a
+// high-priority stream ahead of the bulk trailing update, which stays on the caller's stream.
+//   hp step k: wait next[k-1];  apply V_k -> columns of panel k+1;  factor panel k+1 (V -> vpk[(k+1)%3])   set 1
+//   st step k: wait panel[k];   (a) apply V_k -> columns of panel k+2, signal next[k];
+//                               (b) apply V_k -> everything right of panel k+2 (T reused)                    set 0
+// Every column block receives every V exactly once and in order; the panel chain only depends on the
+// small (a) parts, i.e. it has two bulk updates of slack.  Three V buffers: V_{k+2} replaces V_{k-1},
+// whose last reader (b)_{k-1} precedes (a)_k on st.
+static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
+                                double* alpha, const std::vector<Panel>& panels) {
+    const int64_t lend = col0 + nl;
+    const int K = (int)panels.size();
+    cudaStream_t hp = c->hp_stream;
+    std::vector<cudaEvent_t> evPanel(K), evNext(K), evBulk(K);
+    const unsigned evflags = c->la_trace ? cudaEventDefault : cudaEventDisableTiming;
+    for (int k = 0; k < K; ++k) {
+        CU(cudaEventCreateWithFlags(&evPanel[k], evflags));
+        CU(cudaEventCreateWithFlags(&evNext[k], evflags));
+        CU(cudaEventCreateWithFlags(&evBulk[k], evflags));
+    }
+    const int maxch = c->vta_max_chunks > 0 ? c->vta_max_chunks : 24;
+    int rc = 0;
+    do {
+        cudaEvent_t fork;
+        if (cudaEventCreateWithFlags(&fork, evflags) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+        cudaEventRecord(fork, st);
+        cudaStreamWaitEvent(hp, fork, 0);                          // hp starts after everything already queued on st
+        if ((rc = factor_outer_panel(c, hp, c->vpk2[0], c->ws[1], panels[0], m, col0, A, lda, alpha))) break;
+        if ((rc = mirror_panel_to_host(c, hp, panels[0], m, col0, A, lda))) break;
+        cudaEventRecord(evPanel[0], hp);
+        for (int k = 0; k < K && !rc; ++k) {
+            const Panel& p = panels[k];
+            const PanelGeom g = panel_geom(p, m);
+            const double* vk = c->vpk2[k % 3];
+            const int64_t t0 = p.c + p.kb;                                               // first trailing column
+            const int64_t t1 = k + 1 < K ? panels[k + 1].c + panels[k + 1].kb : t0;      // end of panel k+1
+            const int64_t t2 = k + 2 < K ? panels[k + 2].c + panels[k + 2].kb : t1;      // end of panel k+2
+            if (k + 1 < K) {
+                if (k > 0) cudaStreamWaitEvent(hp, evNext[k - 1], 0);   // panel k+1's columns carry V_0..V_{k-1}
+                if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda,
+                                                (int)(t1 - t0)))) break;
+                if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
+                if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
+                cudaEventRecord(evPanel[k + 1], hp);
+            }
+            cudaStreamWaitEvent(st, evPanel[k], 0);
+            bool have_T = false;
+            if (t2 > t1) {
+                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (t1 - col0) * lda + g.r0, lda,
+                                                (int)(t2 - t1), maxch))) break;
+                have_T = true;
+            }
+            cudaEventRecord(evNext[k], st);
+            if (lend > t2)
+                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (t2 - col0) * lda + g.r0, lda,
+                                                (int)(lend - t2), maxch, have_T))) break;
+            cudaEventRecord(evBulk[k], st);
+        }
+        if (rc) { cudaEventDestroy(fork); break; }
+        cudaStreamWaitEvent(st, evPanel[K - 1], 0);                // join: alpha and the last panel come from hp
+        if (c->la_trace) {
+            cudaStreamSynchronize(st);
+            cudaStreamSynchronize(hp);
+            c->la_times.assign((size_t)K * 3, 0.f);
+            for (int k = 0; k < K; ++k) {
+                cudaEventElapsedTime(&c->la_times[3 * k + 0], fork, evPanel[k]);
+                cudaEventElapsedTime(&c->la_times[3 * k + 1], fork, evNext[k]);
+                cudaEventElapsedTime(&c->la_times[3 * k + 2], fork, evBulk[k]);
+            }
+        }
+        cudaEventDestroy(fork);
+    } while (0);
+    // events may be destroyed once recorded/waited on: the work they order is already enqueued
+    for (int k = 0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
+    if (!rc) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = set_err(1000 + (int)e, "look-ahead enqueue failed: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
 static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, int64_t col0, int64_t nl, double* A,
                       int64_t lda, double* alpha, int nb) {
     std::vector<int64_t> col0s, nls;
@@ -391,38 +577,10 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
     TRY(ensure_workspace(c, m, nlmax));
     std::vector<Panel> panels;
     build_panels(col0s, nls, nb, panels);
-    const int64_t lend = col0 + nl;
-    for (const Panel& p : panels) {
-        const int64_t r0 = p.c & ~(int64_t)31;             // window start: 32-row aligned for the TMA chunks
-        const int64_t rows = m - r0;                        // valid window rows
-        const int64_t vrows = rup(rows, 128);
-        const int nbp = (int)rup(p.kb, IB);
-        if (c->rank == p.owner) {
-            for (int o = 0; o < p.kb; o += IB) {
-                const int ib = std::min(IB, p.kb - o);
-                const int64_t cs = p.c + o;                                   // global column == pivot row
-                double* P = A + (cs - col0) * lda + cs;
-                TRY(launch_panel(c, st, P, lda, m - cs, ib, alpha + cs, o, cs - r0, vrows));
-                const int rem = p.kb - (o + ib);
-                if (rem > 0)   // update the rest of the outer panel with this sub-panel's reflectors
-                    TRY(apply_block_reflector(c, st, o, IB, rows, cs - r0, A + (cs + ib - col0) * lda + r0, lda, rem));
-            }
-            if (nbp > IB && nbp < NBMAX) {   // zero the V columns the 128-wide kernels read beyond nbp
-                k_vpk_zero_cols<<<2 * c->sms, 256, 0, st>>>(c->vpk, vrows / KC1, nbp, NBMAX);
-                TRY(post(c, st, "k_vpk_zero_cols"));
-            }
-        }
-        if (c->nranks > 1) {
-            // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
-            NC(g_nccl.Broadcast(c->vpk, c->vpk, (size_t)(vrows / KC1) * VPK_CHUNK, ncclFloat64, p.owner, c->comm, st));
-            NC(g_nccl.Broadcast(alpha + p.c, alpha + p.c, (size_t)p.kb, ncclFloat64, p.owner, c->comm, st));
-        }
-        // trailing update of the local columns right of the panel (S:198-213 for nb columns at once)
-        const int64_t t0 = std::max(p.c + p.kb, col0);
-        if (t0 < lend)
-            TRY(apply_block_reflector(c, st, 0, nbp, rows, p.c - r0, A + (t0 - col0) * lda + r0, lda, (int)(lend - t0)));
-    }
-    return 0;
+    if (panels.empty()) return 0;
+    if (c->nranks == 1 && c->lookahead && panels.size() > 1 && !c->sync && !c->profile)
+        return qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels);
+    return qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels);
 }
 
 // qr!: unblocked driver (nb == 1): one reflector per step, as the reference does it (S:127-144)
@@ -480,9 +638,9 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
         const int64_t rows = m - r0, vrows = rup(rows, 128);
         const int nbp = kb <= IB ? IB : NBMAX;
         dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbp);
-        k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk, 0, cs - r0, vrows);
+        k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk2[0], 0, cs - r0, vrows);
         TRY(post(c, st, "k_pack"));
-        TRY(apply_block_reflector(c, st, 0, nbp, rows, cs - r0, b + r0, ldb, nrhs));
+        TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbp, rows, cs - r0, b + r0, ldb, nrhs));
     }
     return 0;
 }
@@ -523,6 +681,12 @@ static int create_common(dhqr_handle* h, int device) {
     c->sms = prop.multiProcessorCount;
     CU(cudaMalloc((void**)&c->d_i64, sizeof(int64_t) * 2 * 1025));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->hp_stream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreateWithFlags(&c->ev0, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev1, cudaEventDisableTiming));
     *h = c;
@@ -562,9 +726,15 @@ int dhqr_destroy(dhqr_handle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    cudaFree(c->vpk); cudaFree(c->wpart); cudaFree(c->wsum); cudaFree(c->ypk); cudaFree(c->linv); cudaFree(c->cells);
+    cudaFree(c->vpk2[2]);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
+    }
+    cudaFree(c->cells); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
+    if (c->hp_stream) cudaStreamDestroy(c->hp_stream);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -584,6 +754,24 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->sync = value ? 1 : 0;
     } else if (!strcmp(key, "profile")) {
         c->profile = value ? 1 : 0;
+    } else if (!strcmp(key, "lookahead")) {
+        c->lookahead = value ? 1 : 0;
+    } else if (!strcmp(key, "cvy_stagger")) {
+        c->cvy_stagger = value ? 1 : 0;
+    } else if (!strcmp(key, "la_trace")) {
+        c->la_trace = value ? 1 : 0;
+    } else if (!strcmp(key, "vta_max_chunks")) {
+        c->vta_max_chunks = (int)value;
+    } else if (!strcmp(key, "panel_backoff")) {
+        c->panel_backoff = (int)value;
+    } else if (!strcmp(key, "panel_trace")) {
+        if (value && !c->panel_trace) {
+            CU(cudaMalloc((void**)&c->panel_trace, sizeof(long long) * (size_t)PANEL_MAXG * IB * 8));
+            CU(cudaMemset(c->panel_trace, 0, sizeof(long long) * (size_t)PANEL_MAXG * IB * 8));
+        } else if (!value && c->panel_trace) {
+            CU(cudaFree(c->panel_trace));
+            c->panel_trace = nullptr;
+        }
     } else {
         return set_err(-2, "unknown option '%s'", key);
     }
@@ -598,6 +786,7 @@ int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
     else if (!strcmp(key, "panel_ctas")) *value = c->panel_ctas;
     else if (!strcmp(key, "sync")) *value = c->sync;
     else if (!strcmp(key, "profile")) *value = c->profile;
+    else if (!strcmp(key, "lookahead")) *value = c->lookahead;
     else if (!strcmp(key, "sms")) *value = c->sms;
     else if (!strcmp(key, "rank")) *value = c->rank;
     else if (!strcmp(key, "nranks")) *value = c->nranks;
@@ -735,10 +924,19 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     double* dal = c->hostA + (size_t)ldd * n;
     cudaStream_t st = c->copy_stream;
     CU(cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice, st));
-    TRY(dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st));
-    CU(cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    const bool blocked = (nb != 1);
+    if (blocked) { c->mirror_host = hA; c->mirror_lda = lda; }      // panels stream back while later panels are factored
+    int rc = dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st);
+    c->mirror_host = nullptr;
+    if (rc == 0 && !blocked)
+        rc = (cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st) == cudaSuccess) ? 0 : set_err(1001, "D2H failed");
+    if (rc == 0) rc = (cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess) ? 0 : set_err(1001, "D2H failed");
+    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
+    for (cudaEvent_t ev : c->panel_events) cudaEventDestroy(ev);
+    c->panel_events.clear();
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return set_err(1000 + (int)e1, "qr_host: %s", cudaGetErrorString(e1));
+    if (e2 != cudaSuccess) return set_err(1000 + (int)e2, "qr_host D2H: %s", cudaGetErrorString(e2));
     return 0;
 }
 
@@ -811,10 +1009,10 @@ int dhqr_k_block_reflector_f64(dhqr_handle c, int64_t rows, int nbp, const doubl
     const int nbk = nbp <= IB ? IB : NBMAX;
     const int64_t vrows = rup(rows, 128);
     dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbk);
-    k_pack<<<grid, 256, 0, st>>>(dV, ldv, rows, nbp, 0, c->vpk, 0, 0, vrows);
+    k_pack<<<grid, 256, 0, st>>>(dV, ldv, rows, nbp, 0, c->vpk2[0], 0, 0, vrows);
     TRY(post(c, st, "k_pack"));
-    TRY(apply_block_reflector(c, st, 0, nbk, rows, row_lo, dC, ldc, ncols));
-    if (d_linv_out) CU(cudaMemcpyAsync(d_linv_out, c->linv, sizeof(double) * (size_t)nbk * nbk, cudaMemcpyDeviceToDevice, st));
+    TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbk, rows, row_lo, dC, ldc, ncols));
+    if (d_linv_out) CU(cudaMemcpyAsync(d_linv_out, c->ws[0].linv, sizeof(double) * (size_t)nbk * nbk, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -822,13 +1020,20 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     if (!c) return set_err(-1, "null handle");
     if (!which) return set_err(-2, "null name");
     if (!d_dst) return set_err(-3, "null destination");
+    if (!strcmp(which, "la_times")) {   // host-side list: converted to doubles and copied to the device buffer
+        std::vector<double> t(c->la_times.begin(), c->la_times.end());
+        if ((size_t)nelems < t.size()) return set_err(-4, "need %zu elements", t.size());
+        CU(cudaMemcpy(d_dst, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    }
     const double* src = nullptr;
     size_t have = 0;
-    if (!strcmp(which, "wpart")) { src = c->wpart; have = c->wpart_elems; }
-    else if (!strcmp(which, "wsum")) { src = c->wsum; have = c->wsum_elems; }
-    else if (!strcmp(which, "ypk")) { src = c->ypk; have = c->ypk_elems; }
-    else if (!strcmp(which, "linv")) { src = c->linv; have = (size_t)NBMAX * NBMAX; }
-    else if (!strcmp(which, "vpk")) { src = c->vpk; have = c->vpk_elems; }
+    if (!strcmp(which, "wpart")) { src = c->ws[0].wpart; have = c->ws[0].wpart_elems; }
+    else if (!strcmp(which, "wsum")) { src = c->ws[0].wsum; have = c->ws[0].wsum_elems; }
+    else if (!strcmp(which, "ypk")) { src = c->ws[0].ypk; have = c->ws[0].ypk_elems; }
+    else if (!strcmp(which, "linv")) { src = c->ws[0].linv; have = (size_t)NBMAX * NBMAX; }
+    else if (!strcmp(which, "vpk")) { src = c->vpk2[0]; have = c->vpk_elems[0]; }
+    else if (!strcmp(which, "panel_trace")) { src = (const double*)c->panel_trace; have = c->panel_trace ? (size_t)PANEL_MAXG * IB * 8 : 0; }
     else return set_err(-2, "unknown buffer '%s'", which);
     if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);
     CU(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)nelems, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -845,7 +1050,7 @@ int dhqr_k_panel_f64(dhqr_handle c, int64_t rows, int ncols, double* dP, int64_t
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(c, rows, ncols));
-    return launch_panel(c, st, dP, ldp, rows, ncols, d_alpha, 0, 0, rup(rows, 128));
+    return launch_panel(c, st, c->vpk2[0], dP, ldp, rows, ncols, d_alpha, 0, 0, rup(rows, 128));
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ namespace dhqr {
 constexpr int KC = 32;        // K-chunk: rows per stage in gemm_vta, V columns per stage in gemm_cvy
 constexpr int LDK = KC + 4;   // padded leading dim of [column][k] smem tiles: 36 doubles (288 B), 36 % 16 == 4
 constexpr int IB = 32;        // inner (cooperative) panel width
-constexpr int PANEL_THREADS = 256;
+constexpr int PANEL_THREADS = 512;
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier, TMA bulk copy, fp64 tensor-core MMA
@@ -280,6 +280,9 @@ struct GemmCvyArgs {
     const double* ypk;  // packed Y: [n_tile][k_chunk][64][LDK]
     int nkq;            // k-chunks (of KC columns) to run
     int nkq_alloc;      // k-chunks per n_tile in ypk (tile stride)
+    unsigned int* sm_ticket;   // [#SMs] ever-increasing per-SM counters (phase staggering), may be null
+    int first_wave;     // CTAs with a linear id below this are in the first wave
+    int stagger_cycles; // delay of the odd-ticket CTA of an SM in the first wave
 };
 
 template <int MINB>
@@ -298,6 +301,23 @@ __global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int nit = a.nkq;
+
+    // The two CTAs that share an SM start together and would stay phase-locked (both loading C, both
+    // in the MMA loop, both storing): delay one of each first-wave pair by about half a tile so that
+    // one CTA's C-tile traffic overlaps the other's tensor work for the rest of the kernel.
+    if (a.sm_ticket && (int)(blockIdx.x + blockIdx.y * gridDim.x) < a.first_wave) {
+        __shared__ unsigned int ticket;
+        if (tid == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            ticket = atomicAdd(&a.sm_ticket[smid], 1u);
+        }
+        __syncthreads();
+        if (ticket & 1u) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < a.stagger_cycles) __nanosleep(200);
+        }
+    }
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
 // ------------------------------------------------------------------------------------------------
 // tinv:  Linv = (I + stril(S))^{-1},  S = first NBP ext columns of the reduced Wext.
 //   With |v|^2 = 2 the compact-WY factor obeys T^{-1} = I + striu(V'V), so Linv == T'.
-//   One CTA; 32x32 diagonal blocks by forward substitution, then two levels of
+//   One CTA; 8x8 diagonal blocks by forward substitution, then log2(NBP/8) merge levels
 //   X21 = -X22 (L21 X11).
 // ------------------------------------------------------------------------------------------------
 template <int NBP>
@@ -398,27 +418,29 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
         L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
     }
     __syncthreads();
-    // diagonal 32x32 blocks: X = (I + N)^{-1}; thread = one column of one block
-    constexpr int ND = NBP / 32;
-    if (tid < ND * 32) {
-        const int d = tid >> 5, j = tid & 31;
-        const double* Ld = L + (d * 32) * LDL + d * 32;
-        double* X = T + d * 32 * 33;   // (i,j) at j*33 + i
-        for (int i = 0; i < 32; ++i) X[j * 33 + i] = (i == j) ? 1.0 : 0.0;
-        for (int i = 1; i < 32; ++i) {
+    // diagonal 8x8 blocks: X = (I + N)^{-1} by forward substitution; thread = one column of one block
+    constexpr int NDB = NBP / 8;
+    if (tid < NDB * 8) {
+        const int d = tid >> 3, j = tid & 7;
+        const double* Ld = L + (d * 8) * LDL + d * 8;
+        double* X = T + d * 72;   // (i,j) at j*9 + i
+#pragma unroll
+        for (int i = 0; i < 8; ++i) X[j * 9 + i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
             double accv = 0.0;
-            for (int k = 0; k < i; ++k) accv += Ld[k * LDL + i] * X[j * 33 + k];
-            if (i > j) X[j * 33 + i] = -accv;
+            for (int k = 0; k < i; ++k) accv += Ld[k * LDL + i] * X[j * 9 + k];
+            if (i > j) X[j * 9 + i] = -accv;
         }
     }
     __syncthreads();
-    for (int e = tid; e < ND * 32 * 32; e += blockDim.x) {
-        const int d = e / 1024, r = e % 1024, i = r % 32, j = r / 32;
-        L[(d * 32 + j) * LDL + d * 32 + i] = T[d * 32 * 33 + j * 33 + i];
+    for (int e = tid; e < NDB * 64; e += blockDim.x) {
+        const int d = e / 64, r = e % 64, i = r % 8, j = r / 8;
+        L[(d * 8 + j) * LDL + d * 8 + i] = T[d * 72 + j * 9 + i];
     }
     __syncthreads();
-    // merge levels
-    for (int bs = 32; bs < NBP; bs *= 2) {
+    // merge levels: X21 = -X22 (L21 X11) for every pair of adjacent inverted blocks
+    for (int bs = 8; bs < NBP; bs *= 2) {
         const int npairs = NBP / (2 * bs);
         // T_p = L21 * X11 for every pair p      (bs x bs each; npairs * bs * bs <= 4096 <= scratch)
         for (int e = tid; e < npairs * bs * bs; e += blockDim.x) {
@@ -450,7 +472,7 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
 // ------------------------------------------------------------------------------------------------
 constexpr int YCOLS = 32;
 template <int NBP>
-__global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int na, const double* __restrict__ Linv,
+__global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int woff, int na, const double* __restrict__ Linv,
                                                   double* __restrict__ ypk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sL = reinterpret_cast<double*>(smem_raw);   // [NBP][NBP] col-major
@@ -461,7 +483,7 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws,
     for (int e = tid; e < NBP * NBP; e += blockDim.x) sL[e] = Linv[e];
     for (int e = tid; e < YCOLS * NBP; e += blockDim.x) {
         const int j = e / NBP;
-        sW[e] = (j < nc) ? Ws[(int64_t)(NBP + c0) * NBP + e] : 0.0;
+        sW[e] = (j < nc) ? Ws[(int64_t)(woff + c0) * NBP + e] : 0.0;   // woff = ext column where W starts (NBP, or 0 when T is reused)
     }
     __syncthreads();
     constexpr int TPR = 256 / NBP;           // threads per row (2 for 128, 8 for 32)
@@ -490,10 +512,12 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws,
 //   x'a_c (x = next pivot column, rows > j) for every remaining column c, so that after the exchange
 //   every CTA can form   s=|x|, alpha, f   and   w_c = v'a_c = f (x'a_c - alpha a_c[j])   locally
 //   (S:129-131 and S:208 in one reduction).
-//   The exchange is all-to-all through L2 with self-validating cells (the NCCL "LL" idea): each
-//   8-byte word carries 32 data bits and a 32-bit tag unique to (launch, column), so a reader needs
-//   no fence, no atomic and no barrier — one L2 round trip per column.  Partials are summed in CTA
-//   order (deterministic).  Also writes the packed V block (vpk) for the GEMMs.
+//   The exchange goes through L2 in self-validating cells (the NCCL "LL" idea): every 8-byte word
+//   carries 32 data bits and a 32-bit tag unique to (launch, column) -> no fence, no atomic, no
+//   barrier.  Two levels keep the traffic and the number of pollers small: each CTA publishes its
+//   partials; the owner warp of column c (CTA c % G) sums the G partials in CTA order (deterministic)
+//   and publishes one total; every CTA then polls at most IB totals and IB pivot-row cells.
+//   Also writes the packed V block (vpk) for the GEMMs.
 // ------------------------------------------------------------------------------------------------
 struct PanelArgs {
     double* P;            // panel top-left (row = pivot row of column 0)
@@ -507,8 +531,10 @@ struct PanelArgs {
     int64_t vrows;        // total window rows incl. padding (zero-filled below vtop+mp)
     int rows_per_cta;
     int lds;              // slab leading dimension (>= rows_per_cta, odd)
-    unsigned long long* cells;   // [IB+1 steps][gridDim.x+1][IB][2]
-    uint32_t epoch;       // tags epoch+1 .. epoch+IB+1 belong to this launch
+    unsigned long long* cells;   // [IB steps][(G + 2) * IB cells][2 words]
+    uint32_t epoch;       // tags epoch+1 .. epoch+IB belong to this launch
+    int backoff;          // ns to sleep between polls of a cell that is not there yet (0 = spin)
+    long long* trace;     // optional clock64() stamps [gridDim.x][IB][8] (debugging / tuning); null = off
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long* cell, double v, uint32_t tag) {
@@ -519,96 +545,143 @@ __device__ __forceinline__ void ll_store(unsigned long long* cell, double v, uin
 __device__ __forceinline__ void ll_peek(const unsigned long long* cell, unsigned long long& w0, unsigned long long& w1) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(cell) : "memory");
 }
-__device__ __forceinline__ double ll_finish(const unsigned long long* cell, unsigned long long w0, unsigned long long w1, uint32_t tag) {
-    while ((uint32_t)(w0 >> 32) != tag || (uint32_t)(w1 >> 32) != tag) ll_peek(cell, w0, w1);
+__device__ __forceinline__ double ll_finish(const unsigned long long* cell, unsigned long long w0, unsigned long long w1, uint32_t tag,
+                                            int backoff) {
+    while ((uint32_t)(w0 >> 32) != tag || (uint32_t)(w1 >> 32) != tag) {
+        if (backoff > 0) __nanosleep(backoff);
+        ll_peek(cell, w0, w1);
+    }
     return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
+__device__ __forceinline__ double ll_wait(const unsigned long long* cell, uint32_t tag, int backoff) {
+    unsigned long long w0, w1;
+    ll_peek(cell, w0, w1);
+    return ll_finish(cell, w0, w1, tag, backoff);
+}
 
-constexpr int PANEL_MAXG = 160;                       // max CTAs of the panel kernel
-constexpr int PANEL_GPW = PANEL_MAXG / (PANEL_THREADS / 32);   // cells gathered per thread (20)
+constexpr int PANEL_MAXG = 160;   // max CTAs of the panel kernel (owner gather: 5 cells per lane)
+constexpr int PNW = PANEL_THREADS / 32;
 
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* S = reinterpret_cast<double*>(smem_raw);   // [IB][lds]
-    __shared__ double red[PANEL_THREADS / 32][IB];
-    __shared__ double tot[IB];
-    __shared__ double pv[IB];
+    __shared__ double tot[2][IB];
+    __shared__ double pv[2][IB];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = PANEL_THREADS / 32;
     const int G = gridDim.x, cta = blockIdx.x;
     const int64_t row0 = (int64_t)cta * a.rows_per_cta;
     const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - row0));
     const int lds = a.lds, nc = a.ncols;
-    const size_t step_stride = (size_t)(G + 1) * IB * 2;   // u64 words per step
-    auto cell = [&](int step, int g, int c) { return a.cells + (size_t)step * step_stride + ((size_t)g * IB + c) * 2; };
+    const size_t step_words = ((size_t)G * IB + 2 * IB) * 2;
+    auto pcell = [&](int step, int g, int c) { return a.cells + (size_t)step * step_words + ((size_t)g * IB + c) * 2; };
+    auto tcell = [&](int step, int c) { return a.cells + (size_t)step * step_words + ((size_t)G * IB + c) * 2; };
+    auto vcell = [&](int step, int c) { return a.cells + (size_t)step * step_words + ((size_t)G * IB + IB + c) * 2; };
+    auto clampi = [&](int64_t x) { return x < 0 ? 0 : (x > nr ? nr : (int)x); };
 
     // load slab (coalesced along rows)
-    for (int c = warp; c < nc; c += NW)
+    for (int c = warp; c < nc; c += PNW)
         for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
     __syncthreads();
 
-    // step 0: partial dots of column 0 against every column (all rows), and the pivot row
-    for (int c = warp; c < nc; c += NW) {
-        double acc = 0.0;
-        for (int r = lane; r < nr; r += 32) acc += S[r] * S[c * lds + r];
-        acc = warp_sum(acc);
-        if (lane == 0) ll_store(cell(0, cta, c), acc, a.epoch + 1);
-    }
-    if (cta == 0 && tid < nc) ll_store(cell(0, G, tid), S[tid * lds + 0], a.epoch + 1);
+    // produce(jn): [apply reflector jn-1 to the columns right of jn]  +  partial dots of column jn (rows >= jn)
+    // against the columns >= jn, published as cells of step jn; CTA 0 also publishes row jn (the next pivot row);
+    // owner warps gather the partials of their column and publish the total.
+    auto produce = [&](const int jn, const bool upd, const double f, const double alpha, const int pb) {
+        const uint32_t tag = a.epoch + 1 + jn;
+        const int jp = jn - 1;
+        const int r_lo1 = clampi((int64_t)jn - row0);                 // first local row that enters the dots
+        const int rstart = upd ? clampi((int64_t)jp - row0) : r_lo1;   // first local row touched by the update
+        for (int cA = jn + warp; cA < nc; cA += 2 * PNW) {
+            const int cB = cA + PNW;
+            const bool hasB = cB < nc;
+            const bool updA = upd && cA != jn;                          // column jn itself was updated in step 1
+            const double wA = updA ? f * (tot[pb][cA] - alpha * pv[pb][cA]) : 0.0;
+            const double wB = (upd && hasB) ? f * (tot[pb][cB] - alpha * pv[pb][cB]) : 0.0;
+            double accA = 0.0, accB = 0.0, pivA = 0.0, pivB = 0.0;
+            const double* xcol = S + jn * lds;
+            const double* vcol = S + (upd ? jp : jn) * lds;
+            double* colA = S + cA * lds;
+            double* colB = S + (hasB ? cB : cA) * lds;
+            double accA2 = 0.0, accB2 = 0.0;
+            for (int r = rstart + lane; r < nr; r += 64) {   // two independent rows per iteration (ILP)
+                const int r2 = r + 32;
+                const bool ok2 = r2 < nr;
+                const double xn = xcol[r], xn2 = ok2 ? xcol[r2] : 0.0;
+                const double v = upd ? vcol[r] : 0.0, v2 = (upd && ok2) ? vcol[r2] : 0.0;
+                double tA = colA[r], tB = hasB ? colB[r] : 0.0;
+                double tA2 = ok2 ? colA[r2] : 0.0, tB2 = (ok2 && hasB) ? colB[r2] : 0.0;
+                if (updA) { tA -= v * wA; colA[r] = tA; if (ok2) { tA2 -= v2 * wA; colA[r2] = tA2; } }
+                if (upd && hasB) { tB -= v * wB; colB[r] = tB; if (ok2) { tB2 -= v2 * wB; colB[r2] = tB2; } }
+                if (r >= r_lo1) { accA += xn * tA; accB += xn * tB; }
+                if (ok2 && r2 >= r_lo1) { accA2 += xn2 * tA2; accB2 += xn2 * tB2; }
+                if (row0 + r == jn) { pivA = tA; pivB = tB; }
+                if (ok2 && row0 + r2 == jn) { pivA = tA2; pivB = tB2; }
+            }
+            accA += accA2;
+            accB += accB2;
+            accA = warp_sum(accA);
+            accB = warp_sum(accB);
+            if (lane == 0) {
+                ll_store(pcell(jn, cta, cA), accA, tag);
+                if (hasB) ll_store(pcell(jn, cta, cB), accB, tag);
+            }
+            if (cta == 0) {   // exactly one lane holds row jn of this slab
+                const int64_t d = (int64_t)jn - rstart;
+                if (d >= 0 && d < nr && (d & 31) == lane) {
+                    ll_store(vcell(jn, cA), pivA, tag);
+                    if (hasB) ll_store(vcell(jn, cB), pivB, tag);
+                }
+            }
+            // owner gather (fixed order: lane l sums CTAs l, l+32, ...; then the shuffle tree)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = h ? cB : cA;
+                if ((h && !hasB) || (c % G) != cta) continue;
+                unsigned long long w0[PANEL_MAXG / 32], w1[PANEL_MAXG / 32];
+#pragma unroll
+                for (int t = 0; t < PANEL_MAXG / 32; ++t)
+                    if (lane + 32 * t < G) ll_peek(pcell(jn, lane + 32 * t, c), w0[t], w1[t]);
+                double sum = 0.0;
+#pragma unroll
+                for (int t = 0; t < PANEL_MAXG / 32; ++t)
+                    if (lane + 32 * t < G) sum += ll_finish(pcell(jn, lane + 32 * t, c), w0[t], w1[t], tag, a.backoff);
+                sum = warp_sum(sum);
+                if (lane == 0) ll_store(tcell(jn, c), sum, tag);
+            }
+        }
+    };
+
+    long long* tr = a.trace ? a.trace + (size_t)cta * IB * 8 : nullptr;
+    const long long tstart = clock64();
+    produce(0, false, 0.0, 0.0, 0);
 
     for (int j = 0; j < nc; ++j) {
         const uint32_t tag = a.epoch + 1 + j;
-        // gather: thread (q = warp, c = lane) sums the cells of CTAs q, q+NW, ... in that order.
-        // All loads are issued before any tag is checked -> one L2 round trip when everyone is on time.
-        {
-            double acc = 0.0;
-            if (lane >= j && lane < nc) {
-                unsigned long long w0[PANEL_GPW], w1[PANEL_GPW];
-#pragma unroll
-                for (int t = 0; t < PANEL_GPW; ++t) {
-                    const int g = warp + t * NW;
-                    if (g < G) ll_peek(cell(j, g, lane), w0[t], w1[t]);
-                }
-#pragma unroll
-                for (int t = 0; t < PANEL_GPW; ++t) {
-                    const int g = warp + t * NW;
-                    if (g < G) acc += ll_finish(cell(j, g, lane), w0[t], w1[t], tag);
-                }
-            }
-            red[warp][lane] = acc;
-            if (warp == NW - 1) {
-                double p = 0.0;
-                if (lane >= j && lane < nc) {
-                    unsigned long long x0, x1;
-                    ll_peek(cell(j, G, lane), x0, x1);
-                    p = ll_finish(cell(j, G, lane), x0, x1, tag);
-                }
-                pv[lane] = p;
-            }
+        const int pb = j & 1;
+        if (tr && tid == 0) tr[j * 8 + 0] = clock64() - tstart;   // enter iteration
+        if (warp == 0) {
+            if (lane >= j && lane < nc) tot[pb][lane] = ll_wait(tcell(j, lane), tag, a.backoff);
+            if (tr && lane == j) tr[j * 8 + 7] = clock64() - tstart;   // total of column j arrived
+        } else if (warp == 1) {
+            if (lane >= j && lane < nc) pv[pb][lane] = ll_wait(vcell(j, lane), tag, a.backoff);
+            if (tr && lane == j) tr[j * 8 + 6] = clock64() - tstart;   // pivot element arrived
         }
+        if (tr && tid == 0) tr[j * 8 + 1] = clock64() - tstart;   // warp 0 has its totals
         __syncthreads();
-        if (tid < IB) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < NW; ++q) s += red[q][tid];
-            tot[tid] = s;
-        }
-        __syncthreads();
+        if (tr && tid == 0) tr[j * 8 + 2] = clock64() - tstart;   // block has totals + pivot row
         // S:129-131
-        const double xj = pv[j];
-        const double s = sqrt(tot[j]);
+        const double xj = pv[pb][j];
+        const double s = sqrt(tot[pb][j]);
         const double sg = xj > 0.0 ? 1.0 : (xj < 0.0 ? -1.0 : 0.0);   // sign(0) == 0 as in S:8
         const double alpha = -sg * s;
         const double f = 1.0 / sqrt(s * (s + fabs(xj)));
         if (cta == 0 && tid == 0) a.alpha[j] = alpha;
-        // local index of pivot row j inside this slab (rows before it are finished R entries)
-        const int64_t rj = (int64_t)j - row0;
-        const int r_lo = rj < 0 ? 0 : (rj > nr ? nr : (int)rj);   // first active local row
-        // step 1: v = f (x - alpha e_j) in place; next pivot column updated in place
+        if (tr && tid == 0) tr[j * 8 + 3] = clock64() - tstart + (long long)(f == 12345.678);   // scalars done
+        // step 1: v = f (x - alpha e_j) in place; next pivot column updated in place (rows >= j)
         const bool has_next = j + 1 < nc;
-        const double w1n = has_next ? f * (tot[j + 1] - alpha * pv[j + 1]) : 0.0;
-        for (int r = r_lo + tid; r < nr; r += PANEL_THREADS) {
+        const double w1n = has_next ? f * (tot[pb][j + 1] - alpha * pv[pb][j + 1]) : 0.0;
+        for (int r = clampi((int64_t)j - row0) + tid; r < nr; r += PANEL_THREADS) {
             double x = S[j * lds + r];
             if (row0 + r == j) x -= alpha;
             const double v = f * x;
@@ -616,41 +689,16 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
             if (has_next) S[(j + 1) * lds + r] -= v * w1n;
         }
         __syncthreads();
-        if (has_next) {
-            // rows that enter the next column's dots: global row >= j+1
-            const int64_t rj1 = (int64_t)j + 1 - row0;
-            const int r_lo1 = rj1 < 0 ? 0 : (rj1 > nr ? nr : (int)rj1);
-            // step 2: tasks c = j+1 .. nc-1; c == j+1 is the self-dot, others update + dot
-            for (int c = j + 1 + warp; c < nc; c += NW) {
-                double acc = 0.0;
-                if (c == j + 1) {
-                    for (int r = r_lo1 + lane; r < nr; r += 32) {
-                        const double x = S[c * lds + r];
-                        acc += x * x;
-                    }
-                } else {
-                    const double wc = f * (tot[c] - alpha * pv[c]);
-                    for (int r = r_lo + lane; r < nr; r += 32) {
-                        const double t = S[c * lds + r] - S[j * lds + r] * wc;
-                        S[c * lds + r] = t;
-                        if (r >= r_lo1) acc += S[(j + 1) * lds + r] * t;
-                    }
-                }
-                acc = warp_sum(acc);
-                if (lane == 0) ll_store(cell(j + 1, cta, c), acc, tag + 1);
-            }
-            if (cta == 0) {
-                __syncthreads();
-                if (tid > j && tid < nc) ll_store(cell(j + 1, G, tid), S[tid * lds + (j + 1)], tag + 1);
-            }
-        }
+        if (tr && tid == 0) tr[j * 8 + 4] = clock64() - tstart;   // step 1 done
+        if (has_next) produce(j + 1, true, f, alpha, pb);
+        if (tr && tid == 0) tr[j * 8 + 5] = clock64() - tstart;   // warp 0 finished produce (+ owner gather if any)
     }
     __syncthreads();
     // write back the factored slab, and the packed V block
-    for (int c = warp; c < nc; c += NW)
+    for (int c = warp; c < nc; c += PNW)
         for (int r = lane; r < nr; r += 32) a.P[(int64_t)c * a.ldp + row0 + r] = S[c * lds + r];
     if (a.vpk) {
-        for (int c = warp; c < IB; c += NW) {
+        for (int c = warp; c < IB; c += PNW) {
             const int pc = a.voff + c;
             for (int r = lane; r < nr; r += 32)
                 a.vpk[vpk_index(a.vtop + row0 + r, pc)] = (c < nc && row0 + r >= c) ? S[c * lds + r] : 0.0;

@@ -1,4 +1,4 @@
-"""Quick tuning sweep on the bench workload: panel CTA count / nb, with the per-class profile."""
+"""Quick tuning sweep on the bench workload: look-ahead on/off, panel CTA count, vta chunk cap."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,17 +15,34 @@ def timeit(nb=0, reps=3):
         e0.record(); D.householder_(A, al, nb); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-def profile(nb=0):
-    h.set_option("profile", 1); D.fill_uniform_(A, 0); torch.cuda.synchronize(); h.profile_reset()
-    D.householder_(A, al, nb); torch.cuda.synchronize(); p = h.profile(); h.set_option("profile", 0)
-    return {k: (round(v["ms"], 2), v["count"], round(v["work"] / v["ms"] / 1e9, 1) if k.startswith("k_gemm") and v["ms"] > 0 else None) for k, v in p.items()}
-for pc in [0, 148, 128, 96, 74, 64, 48, 32]:
-    h.set_option("panel_ctas", pc)
+def resid():
+    A0 = D.colmajor_empty(m, n, dev); D.fill_uniform_(A0, 0)
+    R = torch.zeros(m, n, dtype=torch.float64, device=dev)
+    R[:n] = torch.triu(A[:n], 1) + torch.diag(al)
+    for k in range(((n - 1) // 128) * 128, -1, -128):
+        kb = min(128, n - k); V = torch.tril(A[k:, k:k + kb])
+        T = torch.linalg.inv(torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1))
+        R[k:] -= V @ (T @ (V.T @ R[k:]))
+    return float(torch.linalg.norm(R - A0) / torch.linalg.norm(A0))
+def show(tag):
     t = timeit()
-    print(f"panel_ctas={pc}: {t:.2f} ms  {fl / t / 1e9:.2f} TFLOP/s", flush=True)
+    print(f"{tag}: {t:.2f} ms  {fl / t / 1e9:.2f} TFLOP/s", flush=True)
+h.set_option("lookahead", 0); show("serial")
+h.set_option("lookahead", 1); show("lookahead default")
+print("   resid (lookahead):", resid(), flush=True)
+for pc in (96, 64):
+    h.set_option("panel_ctas", pc); show(f"lookahead panel_ctas={pc}")
 h.set_option("panel_ctas", 0)
-print("profile nb=128:", json.dumps(profile()), flush=True)
-for nb in [32, 64, 96]:
-    t = timeit(nb)
-    print(f"nb={nb}: {t:.2f} ms  {fl / t / 1e9:.2f} TFLOP/s", flush=True)
-print("profile nb=64:", json.dumps(profile(64)), flush=True)
+for mc in (8, 16, 48, 1000):
+    h.set_option("vta_max_chunks", mc); show(f"lookahead vta_max_chunks={mc}")
+h.set_option("vta_max_chunks", 0)
+# determinism of the look-ahead schedule
+D.fill_uniform_(A, 0); D.householder_(A, al, 0); torch.cuda.synchronize(); A1 = A.clone()
+D.fill_uniform_(A, 0); D.householder_(A, al, 0); torch.cuda.synchronize()
+print("   lookahead bitwise repeatable:", bool(torch.equal(A, A1)), flush=True)
+h.set_option("cvy_stagger", 0); show("lookahead, cvy_stagger=0")
+h.set_option("cvy_stagger", 1); show("lookahead, cvy_stagger=1")
+h.set_option("lookahead", 0)
+h.set_option("cvy_stagger", 0); show("serial, cvy_stagger=0")
+h.set_option("cvy_stagger", 1); show("serial, cvy_stagger=1")
+h.set_option("lookahead", 1)
