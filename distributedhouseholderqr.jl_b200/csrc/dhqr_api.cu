@@ -338,7 +338,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
 // ------------------------------------------------------------------------------------------------
 static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P, int64_t ldp, int64_t mp, int ncols,
                         double* alpha, int voff, int64_t vtop, int64_t vrows) {
-    int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->nranks == 1 && c->lookahead ? 64 : c->sms);
+    int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->lookahead ? 64 : c->sms);
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
@@ -486,14 +486,17 @@ static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_
     return 0;
 }
 
-// look-ahead (single GPU): the panel chain (latency bound: one grid-wide exchange per column) runs on a
-// high-priority stream ahead of the bulk trailing update, which stays on the caller's stream.
-//   hp step k: wait next[k-1];  apply V_k -> columns of panel k+1;  factor panel k+1 (V -> vpk[(k+1)%3])   set 1
-//   st step k: wait panel[k];   (a) apply V_k -> columns of panel k+2, signal next[k];
-//                               (b) apply V_k -> everything right of panel k+2 (T reused)                    set 0
-// Every column block receives every V exactly once and in order; the panel chain only depends on the
-// small (a) parts, i.e. it has two bulk updates of slack.  Three V buffers: V_{k+2} replaces V_{k-1},
-// whose last reader (b)_{k-1} precedes (a)_k on st.
+// look-ahead: the panel chain (latency bound: one grid-wide exchange per column) runs on a high-priority
+// stream ahead of the bulk trailing update, which stays on the caller's stream.  SPMD over ranks: the owner
+// of a panel factors it, the packed V block is broadcast on the high-priority stream (the only stream that
+// issues collectives), every rank updates its own columns.
+//   hp step k: wait next[k-1];  owner(k+1): apply V_k -> columns of panel k+1, factor panel k+1 (V -> vpk[(k+1)%3]);
+//              broadcast vpk[(k+1)%3] + alpha slice;  signal panel[k+1]                                    set 1
+//   st step k: wait panel[k];   (a) apply V_k -> local columns of panel k+2, signal next[k];
+//                               (b) apply V_k -> local columns right of panel k+2 (T reused)                set 0
+// Every column block receives every V exactly once and in order; the panel chain only depends on the small
+// (a) parts, i.e. it has two bulk updates of slack.  Three V buffers: V_{k+2} replaces V_{k-1}, whose last
+// reader (b)_{k-1} precedes (a)_k on st (hence the wait on next[k-1] on every rank before the broadcast).
 static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
                                 double* alpha, const std::vector<Panel>& panels) {
     const int64_t lend = col0 + nl;
@@ -507,15 +510,30 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         CU(cudaEventCreateWithFlags(&evBulk[k], evflags));
     }
     const int maxch = c->vta_max_chunks > 0 ? c->vta_max_chunks : 24;
+    // local intersection of the global column range [a, b) -> pointer + count
+    auto clip = [&](int64_t a, int64_t b, int64_t& lo, int64_t& hi) { lo = std::max(a, col0); hi = std::min(b, lend); return hi > lo; };
+    // publish panel k (already factored on its owner into vpk[k%3]) to every rank; hp stream
+    auto publish = [&](int k) -> int {
+        if (c->nranks > 1) {
+            const PanelGeom g = panel_geom(panels[k], m);
+            double* v = c->vpk2[k % 3];
+            NC(g_nccl.Broadcast(v, v, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, panels[k].owner, c->comm, hp));
+            NC(g_nccl.Broadcast(alpha + panels[k].c, alpha + panels[k].c, (size_t)panels[k].kb, ncclFloat64, panels[k].owner, c->comm, hp));
+        }
+        CU(cudaEventRecord(evPanel[k], hp));
+        return 0;
+    };
     int rc = 0;
+    cudaEvent_t fork = nullptr;
     do {
-        cudaEvent_t fork;
         if (cudaEventCreateWithFlags(&fork, evflags) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
         cudaEventRecord(fork, st);
         cudaStreamWaitEvent(hp, fork, 0);                          // hp starts after everything already queued on st
-        if ((rc = factor_outer_panel(c, hp, c->vpk2[0], c->ws[1], panels[0], m, col0, A, lda, alpha))) break;
-        if ((rc = mirror_panel_to_host(c, hp, panels[0], m, col0, A, lda))) break;
-        cudaEventRecord(evPanel[0], hp);
+        if (c->rank == panels[0].owner) {
+            if ((rc = factor_outer_panel(c, hp, c->vpk2[0], c->ws[1], panels[0], m, col0, A, lda, alpha))) break;
+            if ((rc = mirror_panel_to_host(c, hp, panels[0], m, col0, A, lda))) break;
+        }
+        if ((rc = publish(0))) break;
         for (int k = 0; k < K && !rc; ++k) {
             const Panel& p = panels[k];
             const PanelGeom g = panel_geom(p, m);
@@ -523,28 +541,32 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             const int64_t t0 = p.c + p.kb;                                               // first trailing column
             const int64_t t1 = k + 1 < K ? panels[k + 1].c + panels[k + 1].kb : t0;      // end of panel k+1
             const int64_t t2 = k + 2 < K ? panels[k + 2].c + panels[k + 2].kb : t1;      // end of panel k+2
+            int64_t lo, hi;
             if (k + 1 < K) {
-                if (k > 0) cudaStreamWaitEvent(hp, evNext[k - 1], 0);   // panel k+1's columns carry V_0..V_{k-1}
-                if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda,
-                                                (int)(t1 - t0)))) break;
-                if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
-                if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
-                cudaEventRecord(evPanel[k + 1], hp);
+                if (k > 0) cudaStreamWaitEvent(hp, evNext[k - 1], 0);   // panel k+1's columns carry V_0..V_{k-1}; vpk[(k+1)%3] is free
+                if (c->rank == panels[k + 1].owner) {
+                    if (clip(t0, t1, lo, hi))
+                        if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
+                                                        lda, (int)(hi - lo)))) break;
+                    if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
+                    if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
+                }
+                if ((rc = publish(k + 1))) break;
             }
             cudaStreamWaitEvent(st, evPanel[k], 0);
             bool have_T = false;
-            if (t2 > t1) {
-                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (t1 - col0) * lda + g.r0, lda,
-                                                (int)(t2 - t1), maxch))) break;
+            if (clip(t1, t2, lo, hi)) {
+                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
+                                                (int)(hi - lo), maxch))) break;
                 have_T = true;
             }
             cudaEventRecord(evNext[k], st);
-            if (lend > t2)
-                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (t2 - col0) * lda + g.r0, lda,
-                                                (int)(lend - t2), maxch, have_T))) break;
+            if (clip(t2, lend, lo, hi))
+                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
+                                                (int)(hi - lo), maxch, have_T))) break;
             cudaEventRecord(evBulk[k], st);
         }
-        if (rc) { cudaEventDestroy(fork); break; }
+        if (rc) break;
         cudaStreamWaitEvent(st, evPanel[K - 1], 0);                // join: alpha and the last panel come from hp
         if (c->la_trace) {
             cudaStreamSynchronize(st);
@@ -556,9 +578,9 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                 cudaEventElapsedTime(&c->la_times[3 * k + 2], fork, evBulk[k]);
             }
         }
-        cudaEventDestroy(fork);
     } while (0);
     // events may be destroyed once recorded/waited on: the work they order is already enqueued
+    if (fork) cudaEventDestroy(fork);
     for (int k = 0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
     if (!rc) {
         cudaError_t e = cudaGetLastError();
@@ -578,7 +600,7 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
     std::vector<Panel> panels;
     build_panels(col0s, nls, nb, panels);
     if (panels.empty()) return 0;
-    if (c->nranks == 1 && c->lookahead && panels.size() > 1 && !c->sync && !c->profile)
+    if (c->lookahead && panels.size() > 1 && !c->sync && !c->profile)
         return qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels);
     return qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels);
 }

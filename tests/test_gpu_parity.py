@@ -200,6 +200,29 @@ def test_bitwise_determinism(D, dev):
         assert torch.equal(A, outs[0][0]) and torch.equal(al, outs[0][1])
 
 
+def test_lookahead_and_serial_schedules_agree(D, dev, oracle):
+    # the look-ahead schedule regroups the trailing updates (other split-K partitions) but applies the same
+    # reflectors in the same order: both schedules must agree to rounding and meet the same tolerances
+    h = D.default_handle(0)
+    m, n = 6000, 900
+    res = {}
+    try:
+        for la in (0, 1):
+            h.set_option("lookahead", la)
+            A = D.colmajor_empty(m, n, dev)
+            D.fill_uniform_(A, 5)
+            H = D.qr_(A)
+            torch.cuda.synchronize()
+            res[la] = (A.cpu().numpy(), H.α.cpu().numpy())
+    finally:
+        h.set_option("lookahead", 1)
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-11
+    assert np.abs(res[0][1] - res[1][1]).max() < TOL_A * np.abs(res[0][1]).max()
+    A0 = oracle.np_uniform(5, m, n)
+    for la in (0, 1):
+        assert oracle.qr_residual(A0, np.asfortranarray(res[la][0]), res[la][1]) < TOL_RES
+
+
 def test_block_reflector_kernels(D, dev, oracle):
     # gemm_vta + tinv + ymake + gemm_cvy in isolation against torch fp64 on genuine Householder blocks
     h = D.default_handle(0)
