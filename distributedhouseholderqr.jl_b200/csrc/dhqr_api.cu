@@ -101,7 +101,7 @@ struct dhqr_context {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     // options
-    int nb = 128, panel_ctas = 0, sync = 0, panel_backoff = 0, vta_max_chunks = 0;
+    int nb = 128, panel_ctas = 0, sync = 0, panel_backoff = 0, vta_max_chunks = 0, panel_levels = 2;
     // workspace
     // two V buffers (panel k and panel k+1 live at the same time under look-ahead) and two workspace
     // sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
@@ -306,21 +306,27 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
         K_G1_128<<<grid1, (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
     }
     TRY(post(c, st, small ? "k_gemm_vta32" : "k_gemm_vta128", 2.0 * (double)rows * nbp * ((double)ncols + nv)));
-    pre(c, st);
-    const int64_t nelem = (int64_t)next * NBPK;
-    k_wreduce<<<(unsigned)std::min<int64_t>((nelem + 255) / 256, 8 * c->sms), 256, 0, st>>>(w.wpart, pstride, nsplit, nelem, w.wsum);
-    TRY(post(c, st, "k_wreduce"));
-    if (!reuse_T) {
-        pre(c, st);
-        if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(w.wsum, w.linv);
-        else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(w.wsum, w.linv);
-        TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
-    }
-    pre(c, st);
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
-    if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
-    else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
-    TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
+    if (small && !reuse_T) {
+        pre(c, st);
+        k_mid32<<<ygrid, 512, 0, st>>>(w.wpart, pstride, nsplit, ncols, w.ypk);
+        TRY(post(c, st, "k_mid32"));
+    } else {
+        pre(c, st);
+        const int64_t nelem = (int64_t)next * NBPK;
+        k_wreduce<<<(unsigned)std::min<int64_t>((nelem + 255) / 256, 8 * c->sms), 256, 0, st>>>(w.wpart, pstride, nsplit, nelem, w.wsum);
+        TRY(post(c, st, "k_wreduce"));
+        if (!reuse_T) {
+            pre(c, st);
+            if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(w.wsum, w.linv);
+            else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(w.wsum, w.linv);
+            TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
+        }
+        pre(c, st);
+        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
+        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
+        TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
+    }
     pre(c, st);
     GemmCvyArgs g2;
     g2.C = C; g2.ldc = ldc; g2.rows = rows; g2.row_lo = row_lo; g2.ncols = ncols;
@@ -358,7 +364,7 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P
     a.P = P; a.ldp = ldp; a.mp = mp; a.ncols = ncols; a.alpha = alpha;
     a.vpk = vpk; a.voff = voff; a.vtop = vtop; a.vrows = vrows;
     a.rows_per_cta = (int)rpc; a.lds = lds;
-    a.cells = c->cells; a.epoch = c->ll_epoch; a.trace = c->panel_trace; a.backoff = c->panel_backoff;
+    a.cells = c->cells; a.epoch = c->ll_epoch; a.trace = c->panel_trace; a.backoff = c->panel_backoff; a.levels = c->panel_levels;
     void* args[] = {&a};
     pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
@@ -784,6 +790,9 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->la_trace = value ? 1 : 0;
     } else if (!strcmp(key, "vta_max_chunks")) {
         c->vta_max_chunks = (int)value;
+    } else if (!strcmp(key, "panel_levels")) {
+        if (value != 1 && value != 2) return set_err(-3, "panel_levels must be 1 or 2");
+        c->panel_levels = (int)value;
     } else if (!strcmp(key, "panel_backoff")) {
         c->panel_backoff = (int)value;
     } else if (!strcmp(key, "panel_trace")) {

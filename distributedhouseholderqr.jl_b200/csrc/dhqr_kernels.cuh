@@ -96,6 +96,7 @@ constexpr int LD1 = KC1 + 4;               // 68
 constexpr int VPK_COLS = 128;
 constexpr int VPK_CHUNK = VPK_COLS * LD1;  // doubles per 64-row chunk
 constexpr int YT = 64;                     // ypk column-tile width (== gemm_cvy BN)
+constexpr int YCOLS = 32;                  // columns per k_ymake / k_mid32 CTA
 
 __device__ __host__ __forceinline__ int64_t vpk_index(int64_t wrow, int col) {
     return ((wrow >> 6) * VPK_COLS + col) * LD1 + (wrow & 63);
@@ -406,18 +407,11 @@ __global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
 //   One CTA; 8x8 diagonal blocks by forward substitution, then log2(NBP/8) merge levels
 //   X21 = -X22 (L21 X11).
 // ------------------------------------------------------------------------------------------------
+// in-place inversion of the unit lower-triangular L (smem, element (i,j) at j*LDL + i, strict lower part filled,
+// rest zero) -> L holds (I + stril)^{-1} including the unit diagonal; T = scratch of >= max(NBP*9, NBP*NBP/4... 4224) doubles
 template <int NBP>
-__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv) {
+__device__ __forceinline__ void tinv_core(double* L, double* T, int tid, int nthreads) {
     constexpr int LDL = NBP + 1;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
-    double* T = L + NBP * LDL;                          // scratch, 4 * 32 * 33 doubles
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
-        const int i = e % NBP, j = e / NBP;
-        L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
-    }
-    __syncthreads();
     // diagonal 8x8 blocks: X = (I + N)^{-1} by forward substitution; thread = one column of one block
     constexpr int NDB = NBP / 8;
     if (tid < NDB * 8) {
@@ -434,7 +428,7 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
         }
     }
     __syncthreads();
-    for (int e = tid; e < NDB * 64; e += blockDim.x) {
+    for (int e = tid; e < NDB * 64; e += nthreads) {
         const int d = e / 64, r = e % 64, i = r % 8, j = r / 8;
         L[(d * 8 + j) * LDL + d * 8 + i] = T[d * 72 + j * 9 + i];
     }
@@ -442,26 +436,86 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
     // merge levels: X21 = -X22 (L21 X11) for every pair of adjacent inverted blocks
     for (int bs = 8; bs < NBP; bs *= 2) {
         const int npairs = NBP / (2 * bs);
-        // T_p = L21 * X11 for every pair p      (bs x bs each; npairs * bs * bs <= 4096 <= scratch)
-        for (int e = tid; e < npairs * bs * bs; e += blockDim.x) {
+        for (int e = tid; e < npairs * bs * bs; e += nthreads) {
             const int p = e / (bs * bs), r = e % (bs * bs), i = r % bs, j = r / bs, o = p * 2 * bs;
-            double s = 0.0;
-            for (int k = j; k < bs; ++k) s += L[(o + k) * LDL + o + bs + i] * L[(o + j) * LDL + o + k];
-            T[p * bs * bs + j * bs + i] = s;
+            double sacc = 0.0;
+            for (int k = j; k < bs; ++k) sacc += L[(o + k) * LDL + o + bs + i] * L[(o + j) * LDL + o + k];
+            T[p * bs * bs + j * bs + i] = sacc;
         }
         __syncthreads();
-        // X21 = -X22 * T_p
-        for (int e = tid; e < npairs * bs * bs; e += blockDim.x) {
+        for (int e = tid; e < npairs * bs * bs; e += nthreads) {
             const int p = e / (bs * bs), r = e % (bs * bs), i = r % bs, j = r / bs, o = p * 2 * bs;
-            double s = 0.0;
-            for (int k = 0; k <= i; ++k) s += L[(o + bs + k) * LDL + o + bs + i] * T[p * bs * bs + j * bs + k];
-            L[(o + j) * LDL + o + bs + i] = -s;
+            double sacc = 0.0;
+            for (int k = 0; k <= i; ++k) sacc += L[(o + bs + k) * LDL + o + bs + i] * T[p * bs * bs + j * bs + k];
+            L[(o + j) * LDL + o + bs + i] = -sacc;
         }
         __syncthreads();
     }
+}
+
+template <int NBP>
+__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv) {
+    constexpr int LDL = NBP + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
+    double* T = L + NBP * LDL;                          // scratch, 4 * 32 * 33 doubles
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
+        const int i = e % NBP, j = e / NBP;
+        L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
+    }
+    __syncthreads();
+    tinv_core<NBP>(L, T, tid, blockDim.x);
     for (int e = tid; e < NBP * NBP; e += blockDim.x) {
         const int i = e % NBP, j = e / NBP;
         Linv[e] = (i >= j) ? L[j * LDL + i] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mid32: the whole middle of a 32-wide block update in one launch (the inner-panel updates sit on the
+// critical path of the panel chain, where every launch costs):  split-K reduction of the Gram block and of
+// this CTA's 32 W columns (fixed order), T' = (I + stril(S))^{-1}, Y = -T'W in the packed ypk layout.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp, int64_t pstride, int nsplit, int na,
+                                                  double* __restrict__ ypk) {
+    constexpr int NBP = 32, LDL = 33;
+    __shared__ double L[NBP * LDL];
+    __shared__ double T[1024];
+    __shared__ double sW[YCOLS * NBP];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * YCOLS;
+    // elements 0..1023: Gram block (i, j); 1024..2047: W tile (k, j)
+    for (int e = tid; e < 2048; e += 512) {
+        const bool isS = e < 1024;
+        const int r = e & 1023, i = r % NBP, j = r / NBP;
+        const bool need = isS ? (i > j) : (c0 + j < na);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (need) {
+            const double* src = Wp + (isS ? (int64_t)r : (int64_t)(NBP + c0) * NBP + r);
+            int p = 0;
+            for (; p + 4 <= nsplit; p += 4) {
+                s0 += src[(int64_t)p * pstride];
+                s1 += src[(int64_t)(p + 1) * pstride];
+                s2 += src[(int64_t)(p + 2) * pstride];
+                s3 += src[(int64_t)(p + 3) * pstride];
+            }
+            for (; p < nsplit; ++p) s0 += src[(int64_t)p * pstride];
+        }
+        const double v = (s0 + s1) + (s2 + s3);
+        if (isS) L[j * LDL + i] = v; else sW[r] = v;
+    }
+    __syncthreads();
+    tinv_core<NBP>(L, T, tid, 512);
+    // Y(i, col) = -sum_{k<=i} Linv(i,k) W(k,col);  thread = (i, two columns)
+    const int i = tid % NBP, jg = tid / NBP;   // jg in 0..15
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = jg * 2 + h;
+        double acc = 0.0;
+        for (int k = 0; k <= i; ++k) acc += L[k * LDL + i] * sW[j * NBP + k];
+        const int col = c0 + j;
+        ypk[(int64_t)(col / YT) * (YT * LDK) + (col % YT) * LDK + i] = (col < na) ? -acc : 0.0;   // NKQ == 1
     }
 }
 
@@ -470,7 +524,6 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
 //   the packed layout gemm_cvy stages with one bulk copy:  ypk[col/64][k/32][col%64][LDK].
 //   CTA = YCOLS columns; thread = (row i, a group of the columns).
 // ------------------------------------------------------------------------------------------------
-constexpr int YCOLS = 32;
 template <int NBP>
 __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int woff, int na, const double* __restrict__ Linv,
                                                   double* __restrict__ ypk) {
@@ -534,6 +587,7 @@ struct PanelArgs {
     unsigned long long* cells;   // [IB steps][(G + 2) * IB cells][2 words]
     uint32_t epoch;       // tags epoch+1 .. epoch+IB belong to this launch
     int backoff;          // ns to sleep between polls of a cell that is not there yet (0 = spin)
+    int levels;           // 2: owner warp gathers the partials and publishes a total; 1: every CTA gathers all partials itself
     long long* trace;     // optional clock64() stamps [gridDim.x][IB][8] (debugging / tuning); null = off
 };
 
@@ -637,7 +691,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = h ? cB : cA;
-                if ((h && !hasB) || (c % G) != cta) continue;
+                if (a.levels != 2 || (h && !hasB) || (c % G) != cta) continue;
                 unsigned long long w0[PANEL_MAXG / 32], w1[PANEL_MAXG / 32];
 #pragma unroll
                 for (int t = 0; t < PANEL_MAXG / 32; ++t)
@@ -660,12 +714,31 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         const uint32_t tag = a.epoch + 1 + j;
         const int pb = j & 1;
         if (tr && tid == 0) tr[j * 8 + 0] = clock64() - tstart;   // enter iteration
-        if (warp == 0) {
-            if (lane >= j && lane < nc) tot[pb][lane] = ll_wait(tcell(j, lane), tag, a.backoff);
-            if (tr && lane == j) tr[j * 8 + 7] = clock64() - tstart;   // total of column j arrived
-        } else if (warp == 1) {
-            if (lane >= j && lane < nc) pv[pb][lane] = ll_wait(vcell(j, lane), tag, a.backoff);
-            if (tr && lane == j) tr[j * 8 + 6] = clock64() - tstart;   // pivot element arrived
+        if (a.levels == 2) {
+            if (warp == 0) {
+                if (lane >= j && lane < nc) tot[pb][lane] = ll_wait(tcell(j, lane), tag, a.backoff);
+                if (tr && lane == j) tr[j * 8 + 7] = clock64() - tstart;   // total of column j arrived
+            } else if (warp == 1) {
+                if (lane >= j && lane < nc) pv[pb][lane] = ll_wait(vcell(j, lane), tag, a.backoff);
+                if (tr && lane == j) tr[j * 8 + 6] = clock64() - tstart;   // pivot element arrived
+            }
+        } else {
+            // one hand-off: every CTA sums all G partials of every live column itself (same fixed order as the
+            // owner gather: lane l takes CTAs l, l+32, ...; then the shuffle tree) -> results identical on all CTAs
+            for (int c = j + warp; c < nc; c += PNW) {
+                unsigned long long w0[PANEL_MAXG / 32], w1[PANEL_MAXG / 32];
+#pragma unroll
+                for (int t = 0; t < PANEL_MAXG / 32; ++t)
+                    if (lane + 32 * t < G) ll_peek(pcell(j, lane + 32 * t, c), w0[t], w1[t]);
+                double sum = 0.0;
+#pragma unroll
+                for (int t = 0; t < PANEL_MAXG / 32; ++t)
+                    if (lane + 32 * t < G) sum += ll_finish(pcell(j, lane + 32 * t, c), w0[t], w1[t], tag, a.backoff);
+                sum = warp_sum(sum);
+                if (lane == 0) tot[pb][c] = sum;
+                if (tr && c == j && lane == 0) tr[j * 8 + 7] = clock64() - tstart;
+            }
+            if (warp == PNW - 1 && lane >= j && lane < nc) pv[pb][lane] = ll_wait(vcell(j, lane), tag, a.backoff);
         }
         if (tr && tid == 0) tr[j * 8 + 1] = clock64() - tstart;   // warp 0 has its totals
         __syncthreads();
