@@ -308,8 +308,8 @@ def gpu_residual(torch, D, A, alpha, m, n, dev):
     for k in range(((n - 1) // nbk) * nbk, -1, -nbk):
         kb = min(nbk, n - k)
         V = torch.tril(A[k:, k:k + kb])
-        T = torch.linalg.inv(torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1))
-        R[k:] -= V @ (T @ (V.T @ R[k:]))
+        Tinv = torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1)
+        R[k:] -= V @ torch.linalg.solve_triangular(Tinv, V.T @ R[k:], upper=True)
     A0 = D.colmajor_empty(m, n, dev)
     D.fill_uniform_(A0, 0)
     return float(torch.linalg.norm(R - A0) / torch.linalg.norm(A0))

@@ -112,14 +112,19 @@ struct dhqr_context {
         double* ypk = nullptr;   size_t ypk_elems = 0;                  // packed Y = -T'W
         double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
     } ws[2];
+    double* linv_ring[3] = {nullptr, nullptr, nullptr};               // T' of the outer panels in flight (look-ahead)
     cudaStream_t hp_stream = nullptr;                                   // high-priority stream of the panel chain
     int lookahead = 1;
     int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
     std::vector<float> la_times;                                        // [k][3]: panel k done (hp), next k signalled (st), bulk k done (st), ms since start
     unsigned long long* cells = nullptr;                                // panel exchange cells [IB+1][MAXG+1][IB][2]
     uint32_t ll_epoch = 0;
+    unsigned long long* cells2 = nullptr;                               // exchange cells of the panel kernel's fast path
+    int* fast_stats = nullptr;                                          // [2] fast / fallback panel counters
+    int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
-    int cvy_stagger = 1;
+    int cvy_stagger = 0;
+    int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
@@ -160,7 +165,8 @@ static size_t smem_ymake(int nbp) { return ((size_t)nbp * nbp + YCOLS * nbp) * 8
 
 #define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_NPW>
 #define K_G1_32 k_gemm_vta<32, G1S_BN, 1, 4, G1S_NPW>
-#define K_G2 k_gemm_cvy<2>
+#define K_G2 k_gemm_cvy<2, 2>
+#define K_G2W k_gemm_cvy<4, 2>
 
 static int set_attrs(dhqr_context* c) {
     if (c->attrs_set) return 0;
@@ -168,11 +174,13 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(K_G1_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1(32, G1S_BN)));
     CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
+    CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
     CU(cudaFuncSetAttribute(k_tinv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(32)));
     CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
     CU(cudaFuncSetAttribute(k_ymake<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(32)));
-    CU(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 184 * 1024));
     CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->attrs_set = true;
     return 0;
@@ -207,8 +215,18 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
         TRY(ensure(&w.linv, &w.linv_elems, (size_t)NBMAX * NBMAX));
     }
+    for (int b = 0; b < 3; ++b)
+        if (!c->linv_ring[b]) { size_t o2 = 0; TRY(ensure(&c->linv_ring[b], &o2, (size_t)NBMAX * NBMAX)); }
     size_t one = 0;
     if (!c->sm_ticket) { CU(cudaMalloc((void**)&c->sm_ticket, sizeof(unsigned int) * 1024)); CU(cudaMemset(c->sm_ticket, 0, sizeof(unsigned int) * 1024)); }
+    if (!c->cells2) {
+        const size_t words = (2 * (size_t)(PANEL_MAXG + 1) * (IB * (IB + 1) / 2) + IB * IB + 2 * IB) * 2;
+        CU(cudaMalloc((void**)&c->cells2, words * sizeof(unsigned long long)));
+        CU(cudaMemset(c->cells2, 0, words * sizeof(unsigned long long)));
+        CU(cudaMalloc((void**)&c->fast_stats, 2 * sizeof(int)));
+        CU(cudaMemset(c->fast_stats, 0, 2 * sizeof(int)));
+        c->ll_epoch = 0;
+    }
     if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)IB * (PANEL_MAXG + 2) * IB * 2)); c->ll_epoch = 0; }
     TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
@@ -279,7 +297,8 @@ static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t 
 //   Gram matrix; `w` = the workspace set of the calling chain.
 static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int voff, int nbp,
                                  int64_t rows, int64_t row_lo, double* C, int64_t ldc, int ncols, int max_chunks = 0,
-                                 bool reuse_T = false) {
+                                 bool reuse_T = false, double* linv_io = nullptr) {
+    double* linv = linv_io ? linv_io : w.linv;   // where T' is written (or read from, with reuse_T)
     // reuse_T: w.linv already holds T' of this V (same chain, previous call) -> skip the Gram block and k_tinv
     if (ncols <= 0 || rows <= 0) return 0;
     const bool small = (nbp <= 32);
@@ -309,7 +328,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
     if (small && !reuse_T) {
         pre(c, st);
-        k_mid32<<<ygrid, 512, 0, st>>>(w.wpart, pstride, nsplit, ncols, w.ypk);
+        k_mid32<<<ygrid, 512, 0, st>>>(w.wpart, pstride, nsplit, ncols, w.ypk, linv);
         TRY(post(c, st, "k_mid32"));
     } else {
         pre(c, st);
@@ -318,13 +337,13 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
         TRY(post(c, st, "k_wreduce"));
         if (!reuse_T) {
             pre(c, st);
-            if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(w.wsum, w.linv);
-            else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(w.wsum, w.linv);
+            if (small) k_tinv<32><<<1, 512, smem_tinv(32), st>>>(w.wsum, linv);
+            else k_tinv<128><<<1, 512, smem_tinv(128), st>>>(w.wsum, linv);
             TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
         }
         pre(c, st);
-        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
-        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, w.linv, w.ypk);
+        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, linv, w.ypk);
+        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, linv, w.ypk);
         TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
     }
     pre(c, st);
@@ -334,7 +353,8 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g2.nkq = small ? 1 : (int)(rup(nbp, KC) / KC); g2.nkq_alloc = NBPK / KC;
     g2.sm_ticket = c->cvy_stagger ? c->sm_ticket : nullptr; g2.first_wave = 2 * c->sms; g2.stagger_cycles = 5200 * g2.nkq;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
-    K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
+    if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
+    else K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
     TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
     return 0;
 }
@@ -348,16 +368,17 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
-    while ((size_t)IB * ((size_t)rpc | 1) * 8 > 200 * 1024 && gmax < std::min(c->sms, PANEL_MAXG)) {   // slab too big: use more CTAs
+    while ((size_t)IB * ((size_t)rpc | 1) * 8 > 184 * 1024 && gmax < std::min(c->sms, PANEL_MAXG)) {   // slab too big: use more CTAs
         gmax = std::min(gmax * 2, std::min(c->sms, PANEL_MAXG));
         rpc = rup(std::max<int64_t>((mp + gmax - 1) / gmax, 64), 8);
     }
     const int G = (int)((mp + rpc - 1) / rpc);
     const int lds = (int)rpc | 1;
     const size_t smem = (size_t)IB * lds * 8;
-    if (smem > 200 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
+    if (smem > 184 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
     if (c->ll_epoch > 0xF0000000u) {   // tag space nearly used up: start over with clean cells
         CU(cudaMemsetAsync(c->cells, 0, sizeof(unsigned long long) * (size_t)IB * (PANEL_MAXG + 2) * IB * 2, st));
+        CU(cudaMemsetAsync(c->cells2, 0, sizeof(unsigned long long) * (2 * (size_t)(PANEL_MAXG + 1) * (IB * (IB + 1) / 2) + IB * IB + 2 * IB) * 2, st));
         c->ll_epoch = 0;
     }
     PanelArgs a;
@@ -365,11 +386,12 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P
     a.vpk = vpk; a.voff = voff; a.vtop = vtop; a.vrows = vrows;
     a.rows_per_cta = (int)rpc; a.lds = lds;
     a.cells = c->cells; a.epoch = c->ll_epoch; a.trace = c->panel_trace; a.backoff = c->panel_backoff; a.levels = c->panel_levels;
+    a.cells2 = c->cells2; a.fast = c->panel_fast; a.fast_stats = c->fast_stats;
     void* args[] = {&a};
     pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
     if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_panel failed: %s", cudaGetErrorString(e));
-    c->ll_epoch += IB;
+    c->ll_epoch += IB + 8;
     return post(c, st, "k_panel", 16.0 * (double)mp * ncols);   // work = bytes: panel read once + written once
 }
 
@@ -548,28 +570,36 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             const int64_t t1 = k + 1 < K ? panels[k + 1].c + panels[k + 1].kb : t0;      // end of panel k+1
             const int64_t t2 = k + 2 < K ? panels[k + 2].c + panels[k + 2].kb : t1;      // end of panel k+2
             int64_t lo, hi;
+            double* lk = c->linv_ring[k % 3];
+            bool haveT = false;                                          // T'_k in lk (this rank)
             if (k + 1 < K) {
-                if (k > 0) cudaStreamWaitEvent(hp, evNext[k - 1], 0);   // panel k+1's columns carry V_0..V_{k-1}; vpk[(k+1)%3] is free
+                // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2
+                if (k > 1) cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
                 if (c->rank == panels[k + 1].owner) {
-                    if (clip(t0, t1, lo, hi))
+                    if (clip(t0, t1, lo, hi)) {
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
-                                                        lda, (int)(hi - lo)))) break;
+                                                        lda, (int)(hi - lo), 0, false, lk))) break;
+                        haveT = true;
+                    }
                     if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
                     if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
                 }
                 if ((rc = publish(k + 1))) break;
             }
-            cudaStreamWaitEvent(st, evPanel[k], 0);
-            bool have_T = false;
+            // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1
             if (clip(t1, t2, lo, hi)) {
-                if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
-                                                (int)(hi - lo), maxch))) break;
-                have_T = true;
+                if (k > 0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
+                if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
+                                                (int)(hi - lo), 0, haveT, lk))) break;
+                haveT = true;
             }
-            cudaEventRecord(evNext[k], st);
-            if (clip(t2, lend, lo, hi))
+            cudaEventRecord(evNext[k], hp);                              // T'_k is in the ring (if this rank computed it)
+            cudaStreamWaitEvent(st, evPanel[k], 0);
+            if (clip(t2, lend, lo, hi)) {
+                if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);
                 if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
-                                                (int)(hi - lo), maxch, have_T))) break;
+                                                (int)(hi - lo), maxch, haveT, haveT ? lk : nullptr))) break;
+            }
             cudaEventRecord(evBulk[k], st);
         }
         if (rc) break;
@@ -755,10 +785,11 @@ int dhqr_destroy(dhqr_handle c) {
     cudaDeviceSynchronize();
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->vpk2[2]);
+    for (int b = 0; b < 3; ++b) cudaFree(c->linv_ring[b]);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
-    cudaFree(c->cells); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
+    cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_stream) cudaStreamDestroy(c->hp_stream);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -784,12 +815,17 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->profile = value ? 1 : 0;
     } else if (!strcmp(key, "lookahead")) {
         c->lookahead = value ? 1 : 0;
+    } else if (!strcmp(key, "cvy_warps")) {
+        if (value != 4 && value != 8) return set_err(-3, "cvy_warps must be 4 or 8");
+        c->cvy_warps = (int)value;
     } else if (!strcmp(key, "cvy_stagger")) {
         c->cvy_stagger = value ? 1 : 0;
     } else if (!strcmp(key, "la_trace")) {
         c->la_trace = value ? 1 : 0;
     } else if (!strcmp(key, "vta_max_chunks")) {
         c->vta_max_chunks = (int)value;
+    } else if (!strcmp(key, "panel_fast")) {
+        c->panel_fast = value ? 1 : 0;
     } else if (!strcmp(key, "panel_levels")) {
         if (value != 1 && value != 2) return set_err(-3, "panel_levels must be 1 or 2");
         c->panel_levels = (int)value;
@@ -818,6 +854,12 @@ int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
     else if (!strcmp(key, "sync")) *value = c->sync;
     else if (!strcmp(key, "profile")) *value = c->profile;
     else if (!strcmp(key, "lookahead")) *value = c->lookahead;
+    else if (!strcmp(key, "panel_fast")) *value = c->panel_fast;
+    else if (!strcmp(key, "panels_fast") || !strcmp(key, "panels_fallback")) {
+        int st2[2] = {0, 0};
+        if (c->fast_stats) CU(cudaMemcpy(st2, c->fast_stats, sizeof(st2), cudaMemcpyDeviceToHost));
+        *value = st2[!strcmp(key, "panels_fallback") ? 1 : 0];
+    }
     else if (!strcmp(key, "sms")) *value = c->sms;
     else if (!strcmp(key, "rank")) *value = c->rank;
     else if (!strcmp(key, "nranks")) *value = c->nranks;

@@ -286,10 +286,12 @@ struct GemmCvyArgs {
     int stagger_cycles; // delay of the odd-ticket CTA of an SM in the first wave
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
-    constexpr int BM = 128, BN = YT, WN = 2, NCW = 4, STAGES = 2;
-    constexpr int WTM = 64, WTN = 32;
+template <int WM, int MINB>
+__global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
+    // WM = 2: 4 MMA warps with 64x32 warp tiles;  WM = 4: 8 MMA warps with 32x32 warp tiles (more warps per
+    // scheduler to hide the C-tile loads/stores and the LDS latency)
+    constexpr int BM = 128, BN = YT, WN = 2, NCW = WM * WN, STAGES = 2;
+    constexpr int WTM = BM / WM, WTN = BN / WN;
     constexpr int MI = WTM / 8, NJ = WTN / 8;
     constexpr int VH = KC * LD1;   // doubles per 64-row x 32-col slice
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(5 * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         release_prev_stage(empty, it, STAGES, lane);
-        const double* v = sV + (size_t)s * 2 * VH + wm * VH + fragA;
+        const double* v = sV + (size_t)s * 2 * VH + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
         const double* y = sY + (size_t)s * BN * LDK + wn * WTN * LDK + fragB;
 #pragma unroll
         for (int kk = 0; kk < KC / 4; ++kk) {
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
 // this CTA's 32 W columns (fixed order), T' = (I + stril(S))^{-1}, Y = -T'W in the packed ypk layout.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp, int64_t pstride, int nsplit, int na,
-                                                  double* __restrict__ ypk) {
+                                                  double* __restrict__ ypk, double* __restrict__ linv_out) {
     constexpr int NBP = 32, LDL = 33;
     __shared__ double L[NBP * LDL];
     __shared__ double T[1024];
@@ -507,6 +509,11 @@ __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp,
     }
     __syncthreads();
     tinv_core<NBP>(L, T, tid, 512);
+    if (blockIdx.x == 0)   // keep T' for a later block update with the same V (look-ahead part (b))
+        for (int e = tid; e < NBP * NBP; e += 512) {
+            const int i = e % NBP, j = e / NBP;
+            linv_out[e] = (i >= j) ? L[j * LDL + i] : 0.0;
+        }
     // Y(i, col) = -sum_{k<=i} Linv(i,k) W(k,col);  thread = (i, two columns)
     const int i = tid % NBP, jg = tid / NBP;   // jg in 0..15
 #pragma unroll
@@ -587,6 +594,9 @@ struct PanelArgs {
     unsigned long long* cells;   // [IB steps][(G + 2) * IB cells][2 words]
     uint32_t epoch;       // tags epoch+1 .. epoch+IB belong to this launch
     int backoff;          // ns to sleep between polls of a cell that is not there yet (0 = spin)
+    unsigned long long* cells2;  // exchange cells of the CholeskyQR2 fast path: 2 x [(G+1) x 528] + 1088 cells
+    int fast;             // 1: try CholeskyQR2 + Householder reconstruction first (3 exchanges per panel instead of 32)
+    int* fast_stats;      // optional [2]: number of panels done by the fast path / by the column-wise fallback
     int levels;           // 2: owner warp gathers the partials and publishes a total; 1: every CTA gathers all partials itself
     long long* trace;     // optional clock64() stamps [gridDim.x][IB][8] (debugging / tuning); null = off
 };
@@ -638,6 +648,239 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
     __syncthreads();
 
+    // ============================================================================================
+    // Fast path: CholeskyQR2 + Householder reconstruction (Ballard, Demmel, Grigori, Jacquelin, Nguyen,
+    // Solomonik 2014).  P = Q Rt by two Cholesky-QR passes (2 exchanges: the 32x32 Gram matrices), then the
+    // unique Householder representation of that QR is recovered from the LU factorisation of E - Q S
+    // (S_jj = -sign(Q_jj^(j)) chosen on the fly, pivots U_jj = 1 + |Q_jj^(j)| = tau_j): the top 32x32 block on
+    // CTA 0, one more exchange for its frozen rows, and a row-local triangular solve everywhere else.  In the
+    // reference's storage: v_ij = W_ij^(j) / sqrt(U_jj) (i > j), v_jj = -S_j sqrt(U_jj), alpha_j = S_j Rt_jj,
+    // R_ij = S_i Rt_ij.  Same reflectors as S:127-135 up to rounding (verified against the oracle), but it
+    // squares the panel's condition number on the way: if a Cholesky pivot is not positive or the factor's
+    // diagonal spans more than 1e5 the slab is reloaded and the column-by-column path below runs instead
+    // (that also reproduces the reference's NaN behaviour for zero columns).  The decision is taken from
+    // identical data on every CTA, so it is grid-uniform without another exchange.
+    // ============================================================================================
+    bool done = false;
+    if (a.fast && nc == IB && a.mp >= 2 * IB && a.rows_per_cta >= IB) {
+        constexpr int NGP = IB * (IB + 1) / 2;   // 528 pairs (i >= j)
+        constexpr int LDG = IB + 1;
+        __shared__ double Gm[IB * LDG], R1[IB * LDG], R2[IB * LDG], Wt[IB * LDG];
+        __shared__ double rinv[IB], Sg[IB], Ud[IB], rsq[IB], cl[IB];
+        __shared__ int bad;
+        const size_t reg = (size_t)(G + 1) * NGP;
+        auto c2p = [&](int e, int g, int t) { return a.cells2 + ((size_t)e * reg + (size_t)g * NGP + t) * 2; };
+        auto c2t = [&](int e, int t) { return a.cells2 + ((size_t)e * reg + (size_t)G * NGP + t) * 2; };
+        auto c2u = [&](int idx) { return a.cells2 + (2 * reg + idx) * 2; };   // 1024 frozen-row cells, then Ud[32], Sg[32]
+        if (tid == 0) bad = 0;
+
+        // Gram matrix of the slab -> all-CTA sum in Gm (both triangles); partials summed in CTA order
+        auto gram_exchange = [&](int e, uint32_t tag) {
+            // partial Gram of the slab with 2x2 register tiles: 136 tiles (lower triangle of the 16x16 tile grid)
+            // x 3 interleaved row groups = 408 threads; the 3 partials of an entry are then added in fixed order
+            {
+                constexpr int NT = 136;
+                const int grp = tid / NT, blk = tid % NT;
+                double* Gp = grp == 0 ? Gm : (grp == 1 ? R2 : Wt);     // free scratch at this point (R1 must survive pass 2)
+                if (grp < 3) {
+                    int I = 0;
+                    while ((I + 1) * (I + 2) / 2 <= blk) ++I;
+                    const int J = blk - I * (I + 1) / 2;
+                    const double* a0 = S + (2 * I) * lds;
+                    const double* a1 = a0 + lds;
+                    const double* b0 = S + (2 * J) * lds;
+                    const double* b1 = b0 + lds;
+                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                    int r = grp;
+                    for (; r + 9 < nr; r += 12) {   // 4 rows in flight per iteration (LDS latency), fixed summation order
+                        double x0[4], x1[4], y0[4], y1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { x0[u] = a0[r + 3 * u]; x1[u] = a1[r + 3 * u]; y0[u] = b0[r + 3 * u]; y1[u] = b1[r + 3 * u]; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { c00 += x0[u] * y0[u]; c01 += x0[u] * y1[u]; c10 += x1[u] * y0[u]; c11 += x1[u] * y1[u]; }
+                    }
+                    for (; r < nr; r += 3) {
+                        const double x0 = a0[r], x1 = a1[r], y0 = b0[r], y1 = b1[r];
+                        c00 += x0 * y0; c01 += x0 * y1; c10 += x1 * y0; c11 += x1 * y1;
+                    }
+                    Gp[(2 * I) * LDG + 2 * J] = c00;
+                    Gp[(2 * I) * LDG + 2 * J + 1] = c01;
+                    Gp[(2 * I + 1) * LDG + 2 * J] = c10;
+                    Gp[(2 * I + 1) * LDG + 2 * J + 1] = c11;
+                }
+                __syncthreads();
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                    const int i = x / IB, j = x % IB;
+                    if (j > i) continue;
+                    ll_store(c2p(e, cta, i * (i + 1) / 2 + j), (Gm[i * LDG + j] + R2[i * LDG + j]) + Wt[i * LDG + j], tag);
+                }
+            }
+            for (int q = warp; cta + q * G < NGP; q += PNW) {   // owner of pair t = cta + q G
+                const int t = cta + q * G;
+                unsigned long long w0[PANEL_MAXG / 32], w1[PANEL_MAXG / 32];
+#pragma unroll
+                for (int u = 0; u < PANEL_MAXG / 32; ++u)
+                    if (lane + 32 * u < G) ll_peek(c2p(e, lane + 32 * u, t), w0[u], w1[u]);
+                double sum = 0.0;
+#pragma unroll
+                for (int u = 0; u < PANEL_MAXG / 32; ++u)
+                    if (lane + 32 * u < G) sum += ll_finish(c2p(e, lane + 32 * u, t), w0[u], w1[u], tag, a.backoff);
+                sum = warp_sum(sum);
+                if (lane == 0) ll_store(c2t(e, t), sum, tag);
+            }
+            for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                const int i = x / IB, j = x % IB;
+                if (j > i) continue;
+                const double v = ll_wait(c2t(e, i * (i + 1) / 2 + j), tag, a.backoff);
+                Gm[i * LDG + j] = v;
+                Gm[j * LDG + i] = v;
+            }
+            __syncthreads();
+        };
+        // upper Cholesky factor of Gm -> Rout, 1/diag -> rinv; flags a non-positive / non-finite pivot
+        auto chol = [&](double* Rout) {
+            for (int x = tid; x < IB * LDG; x += PANEL_THREADS) Rout[x] = 0.0;
+            __syncthreads();
+            for (int j = 0; j < IB; ++j) {
+                const double d = Gm[j * LDG + j];
+                const double ri = rsqrt(d);
+                if (tid == 0) {
+                    if (!(d > 0.0) || !(d < 1e300)) bad = 1;
+                    rinv[j] = ri;
+                    Rout[j * LDG + j] = d * ri;
+                }
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                    const int i = x / IB, k = x % IB;
+                    if (i == j && k > j) Rout[j * LDG + k] = Gm[j * LDG + k] * ri;
+                    else if (i > j && k >= i) Gm[i * LDG + k] -= (Gm[j * LDG + i] * ri) * (Gm[j * LDG + k] * ri);
+                }
+                __syncthreads();
+            }
+        };
+        // slab <- slab * R^{-1}  (row-local forward substitution; one row per thread)
+        auto trsm = [&](const double* R) {
+            for (int r = tid; r < nr; r += PANEL_THREADS) {
+                double x[IB];
+#pragma unroll
+                for (int k = 0; k < IB; ++k) x[k] = S[k * lds + r];
+#pragma unroll
+                for (int j = 0; j < IB; ++j) {
+                    const double q = x[j] * rinv[j];
+                    x[j] = q;
+#pragma unroll
+                    for (int k = j + 1; k < IB; ++k) x[k] -= q * R[j * LDG + k];
+                    asm volatile("" ::: "memory");   // keeps ptxas from hoisting all 496 LDS (it spills 4 KB/thread otherwise)
+                }
+#pragma unroll
+                for (int k = 0; k < IB; ++k) S[k * lds + r] = x[k];
+            }
+            __syncthreads();
+        };
+
+        const uint32_t ftag = a.epoch + IB + 1;
+        long long* ftr = a.trace ? a.trace + (size_t)cta * IB * 8 : nullptr;
+        const long long ft0 = clock64();
+        auto stamp = [&](int k) { if (ftr && tid == 0) ftr[k] = clock64() - ft0; };
+        gram_exchange(0, ftag);
+        stamp(1);
+        chol(R1);
+        stamp(2);
+        if (tid == 0 && !bad) {   // conditioning guard on the first factor
+            double dmin = R1[0], dmax = R1[0];
+            for (int j = 1; j < IB; ++j) { dmin = fmin(dmin, R1[j * LDG + j]); dmax = fmax(dmax, R1[j * LDG + j]); }
+            if (!(dmin > 1e-5 * dmax)) bad = 1;
+        }
+        __syncthreads();
+        if (!bad) {
+            trsm(R1);
+            stamp(3);
+            gram_exchange(1, ftag + 1);
+            stamp(4);
+            chol(R2);
+            stamp(5);
+        }
+        __syncthreads();
+        if (!bad) {
+            trsm(R2);
+            stamp(6);
+            // Rt = R2 * R1 (upper) -> Gm
+            for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                const int i = x / IB, k = x % IB;
+                double sacc = 0.0;
+                if (k >= i)
+                    for (int j = i; j <= k; ++j) sacc += R2[i * LDG + j] * R1[j * LDG + k];
+                Gm[i * LDG + k] = sacc;
+            }
+            if (cta == 0) {
+                // LU of the top block of E - Q S on CTA 0: Wt(i,k) = Q(i,k); row j is frozen at step j
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS) Wt[(x / IB) * LDG + (x % IB)] = S[(x % IB) * lds + (x / IB)];
+                __syncthreads();
+                for (int j = 0; j < IB; ++j) {
+                    const double w = Wt[j * LDG + j];
+                    const double sgn = w > 0.0 ? -1.0 : 1.0;
+                    const double u = 1.0 + fabs(w);
+                    if (tid == 0) { Sg[j] = sgn; Ud[j] = u; }
+                    const double f = sgn / u;   // -l_i = f * W(i,j)
+                    for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                        const int i = x / IB, k = x % IB;
+                        if (i > j && k > j) Wt[i * LDG + k] += f * Wt[i * LDG + j] * Wt[j * LDG + k];
+                    }
+                    __syncthreads();
+                }
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS)
+                    if (x % IB > x / IB) ll_store(c2u(x), Wt[(x / IB) * LDG + (x % IB)], ftag + 2);
+                if (tid < IB) { ll_store(c2u(IB * IB + tid), Ud[tid], ftag + 2); ll_store(c2u(IB * IB + IB + tid), Sg[tid], ftag + 2); }
+            } else {
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS)
+                    if (x % IB > x / IB) Wt[(x / IB) * LDG + (x % IB)] = ll_wait(c2u(x), ftag + 2, a.backoff);
+                if (tid < IB) { Ud[tid] = ll_wait(c2u(IB * IB + tid), ftag + 2, a.backoff); Sg[tid] = ll_wait(c2u(IB * IB + IB + tid), ftag + 2, a.backoff); }
+            }
+            __syncthreads();
+            stamp(7);
+            if (tid < IB) { rsq[tid] = 1.0 / sqrt(Ud[tid]); cl[tid] = -Sg[tid] / Ud[tid]; }
+            __syncthreads();
+            // rows below the top block: L2 = M2 U^{-1}, scaled to the reference's |v|^2 = 2 convention
+            for (int r = tid; r < nr; r += PANEL_THREADS) {
+                if (row0 + r < IB) continue;
+                double x[IB];
+#pragma unroll
+                for (int k = 0; k < IB; ++k) x[k] = S[k * lds + r];
+#pragma unroll
+                for (int j = 0; j < IB; ++j) {
+                    const double wj = x[j];
+                    const double l = wj * cl[j];
+                    x[j] = wj * rsq[j];
+#pragma unroll
+                    for (int k = j + 1; k < IB; ++k) x[k] -= l * Wt[j * LDG + k];
+                    asm volatile("" ::: "memory");
+                }
+#pragma unroll
+                for (int k = 0; k < IB; ++k) S[k * lds + r] = x[k];
+            }
+            if (cta == 0) {   // top block: V below the diagonal, R above, alpha
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                    const int i = x / IB, j = x % IB;   // row i, column j
+                    double v;
+                    if (i > j) v = Wt[i * LDG + j] * rsq[j];
+                    else if (i == j) v = -Sg[j] * (Ud[j] * rsq[j]);
+                    else v = Sg[i] * Gm[i * LDG + j];
+                    S[j * lds + i] = v;
+                }
+                if (tid < IB) a.alpha[tid] = Sg[tid] * Gm[tid * LDG + tid];
+            }
+            done = true;
+            stamp(8);
+        } else {
+            // fall back: the slab was modified by the first TRSM at most; reload the untouched panel from memory
+            __syncthreads();
+            for (int c = warp; c < nc; c += PNW)
+                for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
+        }
+        __syncthreads();
+        if (a.fast_stats && cta == 0 && tid == 0) atomicAdd(&a.fast_stats[done ? 0 : 1], 1);
+    }
+
+    if (!done) {
     // produce(jn): [apply reflector jn-1 to the columns right of jn]  +  partial dots of column jn (rows >= jn)
     // against the columns >= jn, published as cells of step jn; CTA 0 also publishes row jn (the next pivot row);
     // owner warps gather the partials of their column and publish the total.
@@ -766,6 +1009,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         if (has_next) produce(j + 1, true, f, alpha, pb);
         if (tr && tid == 0) tr[j * 8 + 5] = clock64() - tstart;   // warp 0 finished produce (+ owner gather if any)
     }
+    }   // if (!done)
     __syncthreads();
     // write back the factored slab, and the packed V block
     for (int c = warp; c < nc; c += PNW)
@@ -781,6 +1025,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                 for (int64_t r = a.vtop + a.mp + lane; r < a.vrows; r += 32) a.vpk[vpk_index(r, pc)] = 0.0;
         }
     }
+    if (a.trace && tid == 0) a.trace[(size_t)cta * IB * 8 + 9] = clock64();   // absolute, for the write-back duration see [10]
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -93,6 +93,8 @@ class COracle:
     def qr(self, a: np.ndarray, nthreads: int = 0):
         """qr!(A::Matrix) (S:311-315): factor ``a`` in place, return (a, alpha)."""
         _check_colmajor(a)
+        if nthreads <= 0:
+            nthreads = min(self.max_threads(), 32)      # plenty for test sizes; bench.py passes its own count
         m, n = a.shape
         alpha = np.zeros(n)
         rc = self.lib.dhqr_oracle_qr(m, n, _fptr(a), a.strides[1] // 8 if n > 0 else max(m, 1), _fptr(alpha), nthreads)

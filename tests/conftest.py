@@ -1,6 +1,10 @@
 import os
 import sys
 
+# the oracle's OpenMP workers must not spin between calls: on a many-core box they starve torch's own CPU side
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -47,8 +47,8 @@ def gpu_residual(D, A, alpha, A0):
     for k in range(((n - 1) // 128) * 128, -1, -128):
         kb = min(128, n - k)
         V = torch.tril(A[k:, k:k + kb])
-        T = torch.linalg.inv(torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1))
-        R[k:] -= V @ (T @ (V.T @ R[k:]))
+        Tinv = torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1)       # T^{-1} = I + striu(V'V)
+        R[k:] -= V @ torch.linalg.solve_triangular(Tinv, V.T @ R[k:], upper=True)
     return float(torch.linalg.norm(R - A0) / torch.linalg.norm(A0))
 
 
@@ -240,7 +240,7 @@ def test_block_reflector_kernels(D, dev, oracle):
         D._lib.call("dhqr_k_block_reflector_f64", h.raw, rows, nbp, vp(dV), rows, row_lo, ncols, vp(dC), rows + ex, vp(dL), sp())
         Vd, Cd = V.to(dev), Cm.to(dev)
         L = torch.eye(nbp, dtype=torch.float64, device=dev) + torch.tril(Vd.T @ Vd, -1)
-        Linv = torch.linalg.inv(L)
+        Linv = torch.linalg.solve_triangular(L, torch.eye(nbp, dtype=torch.float64, device=dev), upper=False)
         Cexp = Cd - Vd @ (Linv @ (Vd.T @ Cd))
         Cexp[:row_lo] = Cd[:row_lo]
         assert float((dL.view(nbk, nbk).T[:nbp, :nbp] - Linv).abs().max()) < 1e-12
@@ -257,6 +257,47 @@ def test_panel_kernel(D, dev, oracle):
         D._lib.call("dhqr_k_panel_f64", h.raw, rows, ncols, vp(dP), rows, vp(dal), sp())
         assert np.abs(dP.cpu().numpy() - Href).max() < 1e-11
         assert np.abs(dal.cpu().numpy() - aref).max() < TOL_A * np.abs(aref).max()
+
+
+def test_panel_fast_path_and_fallback(D, dev, oracle):
+    # CholeskyQR2 + Householder reconstruction must give the reference's reflectors; ill-conditioned, zero and NaN
+    # panels must take the column-by-column fallback (decided on the device) and still match the oracle
+    h = D.default_handle(0)
+    rows = 4096
+
+    def run(P):
+        dP = D.to_colmajor(P, dev)
+        dal = torch.zeros(32, dtype=torch.float64, device=dev)
+        D._lib.call("dhqr_k_panel_f64", h.raw, rows, 32, vp(dP), rows, vp(dal), sp())
+        torch.cuda.synchronize()
+        return dP.cpu().numpy(), dal.cpu().numpy()
+
+    P = oracle.np_uniform(21, rows, 32)
+    Href, aref = oracle.np_qr(P)
+    f0, b0 = h.get_option("panels_fast"), h.get_option("panels_fallback")
+    Hf, af = run(P)
+    assert h.get_option("panels_fast") == f0 + 1 and h.get_option("panels_fallback") == b0
+    try:
+        h.set_option("panel_fast", 0)
+        Hs, as_ = run(P)
+    finally:
+        h.set_option("panel_fast", 1)
+    for Hx, ax in ((Hf, af), (Hs, as_)):
+        assert np.abs(Hx - Href).max() < 1e-11 and np.abs(ax - aref).max() < TOL_A * np.abs(aref).max()
+    # nearly dependent columns: kappa ~ 1e9 > the guard -> fallback, result as accurate as the reference recurrences
+    Pi = P.copy()
+    Pi[:, 7] = Pi[:, 3] + 1e-9 * oracle.np_uniform(22, rows, 1)[:, 0]
+    Hr2, ar2 = oracle.np_qr(Pi)
+    b1 = h.get_option("panels_fallback")
+    Hi, ai = run(Pi)
+    assert h.get_option("panels_fallback") == b1 + 1
+    assert oracle.qr_residual(Pi, np.asfortranarray(Hi), ai) < TOL_RES
+    assert np.abs(ai - ar2).max() < 1e-6 * np.abs(ar2).max()          # alpha_7 is O(1e-9): relative accuracy limited by kappa
+    # zero column: the reference gives f = Inf -> NaN (S:131); the fast path must not "fix" that
+    Pz = P.copy()
+    Pz[:, 5] = 0.0
+    Hz, _ = run(Pz)
+    assert np.isnan(Hz).any()
 
 
 def test_host_buffer_entry_points(D, oracle, coracle):

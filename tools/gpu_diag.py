@@ -162,8 +162,8 @@ if "--quick" not in sys.argv:
         for k in range(((n - 1) // 128) * 128, -1, -128):
             V = torch.tril(dA[k:, k:k + 128])
             S = V.T @ V
-            T = torch.linalg.inv(torch.eye(128, dtype=torch.float64, device=dev) + torch.triu(S, 1))
-            R[k:] -= V @ (T @ (V.T @ R[k:]))
+            Tinv = torch.eye(128, dtype=torch.float64, device=dev) + torch.triu(S, 1)
+            R[k:] -= V @ torch.linalg.solve_triangular(Tinv, V.T @ R[k:], upper=True)
         A0 = D.colmajor_empty(m, n, dev); D.fill_uniform_(A0, 0)
         r = float(torch.linalg.norm(R - A0) / torch.linalg.norm(A0))
         return {"ok": r < 1e-13, "resid": r}

@@ -21,8 +21,8 @@ def resid():
     R[:n] = torch.triu(A[:n], 1) + torch.diag(al)
     for k in range(((n - 1) // 128) * 128, -1, -128):
         kb = min(128, n - k); V = torch.tril(A[k:, k:k + kb])
-        T = torch.linalg.inv(torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1))
-        R[k:] -= V @ (T @ (V.T @ R[k:]))
+        Tinv = torch.eye(kb, dtype=torch.float64, device=dev) + torch.triu(V.T @ V, 1)
+        R[k:] -= V @ torch.linalg.solve_triangular(Tinv, V.T @ R[k:], upper=True)
     return float(torch.linalg.norm(R - A0) / torch.linalg.norm(A0))
 def show(tag):
     t = timeit()
@@ -46,3 +46,7 @@ h.set_option("lookahead", 0)
 h.set_option("cvy_stagger", 0); show("serial, cvy_stagger=0")
 h.set_option("cvy_stagger", 1); show("serial, cvy_stagger=1")
 h.set_option("lookahead", 1)
+for lv, pc in ((1, 64), (1, 48), (1, 40), (2, 48), (2, 40)):
+    h.set_option("panel_levels", lv); h.set_option("panel_ctas", pc); show(f"lookahead panel_levels={lv} panel_ctas={pc}")
+print("   resid:", resid(), flush=True)
+h.set_option("panel_levels", 2); h.set_option("panel_ctas", 0)
