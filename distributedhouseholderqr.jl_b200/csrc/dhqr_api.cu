@@ -124,7 +124,8 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
-    int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
+    int cvy_warps = 8;
+    int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
@@ -134,6 +135,7 @@ struct dhqr_context {
     int64_t launches = 0;
     cudaStream_t copy_stream = nullptr;      // compute stream of the _host_ entry points
     cudaStream_t d2h_stream = nullptr;       // drains finished panels to the host while the factorisation continues
+    cudaStream_t h2d_stream = nullptr;       // uploads the right half while the left half is being factored
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> panel_events;
     // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
@@ -274,13 +276,14 @@ static int post(dhqr_context* c, cudaStream_t st, const char* what, double work 
 // ------------------------------------------------------------------------------------------------
 // splits over the row chunks: fill whole waves of SMs; `max_chunks` (> 0) caps the chunks one CTA runs
 // through (look-ahead wants short-lived CTAs so that the high-priority panel chain gets SMs quickly)
-static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t cap_tiles) {
+static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t cap_tiles, int max_ctas = 0) {
     tiles = std::max(tiles, 1);
     int smin = 1;
     if (max_chunks > 0) smin = std::max(1, (nchunks + max_chunks - 1) / max_chunks);
     int smax = std::max(1, std::min(nchunks / 4, (MAXCTAS_FACTOR * sms) / tiles));
     smax = std::max(smax, std::min(smin + (sms + tiles - 1) / tiles, std::max(1, nchunks / 2)));
     smax = (int)std::min<int64_t>(smax, std::max<int64_t>(1, cap_tiles / tiles));
+    if (max_ctas > 0) smax = std::min(smax, std::max(1, max_ctas / tiles));
     smin = std::min(smin, smax);
     int best = smin;
     double beste = 0.0;
@@ -308,7 +311,8 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     const int next = nv + ncols;
     const int tiles = (next + bn - 1) / bn;
     const int nchunks = (int)((rows + KC1 - 1) / KC1);
-    const int nsplit = pick_splits(tiles, nchunks, c->sms, max_chunks, (int64_t)(w.wpart_elems / ((size_t)bn * NBPK)));
+    const int nsplit = pick_splits(tiles, nchunks, c->sms, max_chunks, (int64_t)(w.wpart_elems / ((size_t)bn * NBPK)),
+                                   (st == c->hp_stream && c->lookahead) ? c->hp_max_ctas : 0);
     const int64_t pstride = (int64_t)tiles * bn * NBPK;
     if ((size_t)(pstride * nsplit) > w.wpart_elems) return set_err(4001, "internal: W partial workspace too small");
     if ((size_t)next * NBPK > w.wsum_elems) return set_err(4003, "internal: W workspace too small");
@@ -740,6 +744,7 @@ static int create_common(dhqr_handle* h, int device) {
     CU(cudaMalloc((void**)&c->d_i64, sizeof(int64_t) * 2 * 1025));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -794,6 +799,7 @@ int dhqr_destroy(dhqr_handle c) {
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -818,6 +824,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "cvy_warps")) {
         if (value != 4 && value != 8) return set_err(-3, "cvy_warps must be 4 or 8");
         c->cvy_warps = (int)value;
+    } else if (!strcmp(key, "hp_max_ctas")) {
+        c->hp_max_ctas = (int)value;
     } else if (!strcmp(key, "cvy_stagger")) {
         c->cvy_stagger = value ? 1 : 0;
     } else if (!strcmp(key, "la_trace")) {
@@ -996,18 +1004,51 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     double* dA = c->hostA;
     double* dal = c->hostA + (size_t)ldd * n;
     cudaStream_t st = c->copy_stream;
-    CU(cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice, st));
     const bool blocked = (nb != 1);
-    if (blocked) { c->mirror_host = hA; c->mirror_lda = lda; }      // panels stream back while later panels are factored
-    int rc = dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st);
+    const int nbe = nb == 0 ? c->nb : nb;
+    // two column halves when the matrix is big enough: the right half uploads while the left half is factored,
+    // then Q_left' is applied to it and the remainder is factored (same reflectors, same flops)
+    const int64_t ns = (blocked && n >= 2048 && m >= n) ? rup(n / 2, nbe) : n;
+    int rc = 0;
+    cudaEvent_t evUp = nullptr, evR12 = nullptr;
+    do {
+        if (cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)ns, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
+        if (ns < n) {
+            cudaEventCreateWithFlags(&evUp, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&evR12, cudaEventDisableTiming);
+            if (cudaMemcpy2DAsync(dA + ns * ldd, (size_t)ldd * 8, hA + ns * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(n - ns),
+                                  cudaMemcpyHostToDevice, c->h2d_stream) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
+            cudaEventRecord(evUp, c->h2d_stream);
+        }
+        if (blocked) { c->mirror_host = hA; c->mirror_lda = lda; }   // finished panels stream back while later panels are factored
+        rc = dhqr_qr_f64(c, m, ns, 0, ns, dA, ldd, dal, nb, st);
+        c->mirror_host = nullptr;
+        if (rc) break;
+        if (ns < n) {
+            cudaStreamWaitEvent(st, evUp, 0);
+            if ((rc = ensure_workspace(c, m, n))) break;
+            if ((rc = apply_qt_local(c, st, m, 0, ns, dA, ldd, dA + ns * ldd, ldd, (int)(n - ns)))) break;   // right half <- Q_left' * right half
+            cudaEventRecord(evR12, st);
+            cudaStreamWaitEvent(c->d2h_stream, evR12, 0);                                                    // R12 is final
+            if (cudaMemcpy2DAsync(hA + ns * lda, (size_t)lda * 8, dA + ns * ldd, (size_t)ldd * 8, (size_t)ns * 8, (size_t)(n - ns),
+                                  cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
+            c->mirror_host = hA + ns * lda + ns; c->mirror_lda = lda;
+            rc = dhqr_qr_f64(c, m - ns, n - ns, 0, n - ns, dA + ns * ldd + ns, ldd, dal + ns, nb, st);
+            c->mirror_host = nullptr;
+            if (rc) break;
+        }
+        if (!blocked)
+            if (cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
+        if (cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
+    } while (0);
     c->mirror_host = nullptr;
-    if (rc == 0 && !blocked)
-        rc = (cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st) == cudaSuccess) ? 0 : set_err(1001, "D2H failed");
-    if (rc == 0) rc = (cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess) ? 0 : set_err(1001, "D2H failed");
-    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
+    cudaError_t e0 = cudaStreamSynchronize(c->h2d_stream), e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
     for (cudaEvent_t ev : c->panel_events) cudaEventDestroy(ev);
     c->panel_events.clear();
+    if (evUp) cudaEventDestroy(evUp);
+    if (evR12) cudaEventDestroy(evR12);
     if (rc) return rc;
+    if (e0 != cudaSuccess) return set_err(1000 + (int)e0, "qr_host H2D: %s", cudaGetErrorString(e0));
     if (e1 != cudaSuccess) return set_err(1000 + (int)e1, "qr_host: %s", cudaGetErrorString(e1));
     if (e2 != cudaSuccess) return set_err(1000 + (int)e2, "qr_host D2H: %s", cudaGetErrorString(e2));
     return 0;

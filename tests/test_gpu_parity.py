@@ -301,7 +301,8 @@ def test_panel_fast_path_and_fallback(D, dev, oracle):
 
 
 def test_host_buffer_entry_points(D, oracle, coracle):
-    for m, n in [(1024, 128), (1001, 37)]:
+    # (4096, 2176) takes the two-half pipeline of dhqr_qr_host_f64 (right half uploads while the left half is factored)
+    for m, n in [(1024, 128), (1001, 37), (4096, 2176)]:
         A0 = coracle.fill_uniform(3, m, n)
         Href = A0.copy(order="F")
         Href, aref = coracle.qr(Href)
