@@ -113,7 +113,8 @@ struct dhqr_context {
         double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
     } ws[2];
     double* linv_ring[3] = {nullptr, nullptr, nullptr};               // T' of the outer panels in flight (look-ahead)
-    cudaStream_t hp_stream = nullptr;                                   // high-priority stream of the panel chain
+    cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
+    cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     int lookahead = 1;
     int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
     std::vector<float> la_times;                                        // [k][3]: panel k done (hp), next k signalled (st), bulk k done (st), ms since start
@@ -541,7 +542,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         CU(cudaEventCreateWithFlags(&evNext[k], evflags));
         CU(cudaEventCreateWithFlags(&evBulk[k], evflags));
     }
-    const int maxch = c->vta_max_chunks > 0 ? c->vta_max_chunks : 24;
+    const int maxch = c->vta_max_chunks;   // 0: no cap on the chunks per gemm_vta CTA (short CTAs did not help the chain)
     // local intersection of the global column range [a, b) -> pointer + count
     auto clip = [&](int64_t a, int64_t b, int64_t& lo, int64_t& hi) { lo = std::max(a, col0); hi = std::min(b, lend); return hi > lo; };
     // publish panel k (already factored on its owner into vpk[k%3]) to every rank; hp stream
@@ -748,7 +749,9 @@ static int create_common(dhqr_handle* h, int device) {
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&c->hp_stream, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->hp_hi, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->hp_lo, cudaStreamNonBlocking, lo));
+        c->hp_stream = c->hp_hi;
     }
     CU(cudaEventCreateWithFlags(&c->ev0, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev1, cudaEventDisableTiming));
@@ -795,7 +798,8 @@ int dhqr_destroy(dhqr_handle c) {
         cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
-    if (c->hp_stream) cudaStreamDestroy(c->hp_stream);
+    if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
+    if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -824,6 +828,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "cvy_warps")) {
         if (value != 4 && value != 8) return set_err(-3, "cvy_warps must be 4 or 8");
         c->cvy_warps = (int)value;
+    } else if (!strcmp(key, "hp_priority")) {
+        c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
     } else if (!strcmp(key, "cvy_stagger")) {
