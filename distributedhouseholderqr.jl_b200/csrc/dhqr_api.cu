@@ -585,6 +585,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
                                                         lda, (int)(hi - lo), 0, false, lk))) break;
                         haveT = true;
+                        cudaEventRecord(evNext[k], hp);                  // T'_k is in the ring: the bulk update may start
                     }
                     if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
                     if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
@@ -594,11 +595,13 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1
             if (clip(t1, t2, lo, hi)) {
                 if (k > 0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
+                const bool hadT = haveT;
                 if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
                                                 (int)(hi - lo), 0, haveT, lk))) break;
                 haveT = true;
+                if (!hadT) cudaEventRecord(evNext[k], hp);               // T'_k came from this apply
             }
-            cudaEventRecord(evNext[k], hp);                              // T'_k is in the ring (if this rank computed it)
+            if (!haveT) cudaEventRecord(evNext[k], hp);                  // keep the event defined (timeline tracing)
             cudaStreamWaitEvent(st, evPanel[k], 0);
             if (clip(t2, lend, lo, hi)) {
                 if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);

@@ -52,9 +52,18 @@ int dhqr_create(dhqr_handle *h, int device);
 int dhqr_create_dist(dhqr_handle *h, int device, const void *unique_id, int rank, int nranks);
 int dhqr_nccl_unique_id(void *out_unique_id);
 int dhqr_destroy(dhqr_handle h);
-/* Tunables: "nb" (outer panel width, multiple of 32 in [32,128], default 128), "panel_ctas"
- * (CTAs of the cooperative panel kernel, 0 = one per SM), "sync" (1 = cudaStreamSynchronize and
- * error-check after every kernel launch; debugging), "profile" (1 = CUDA-event bracket per launch). */
+/* Tunables (dhqr_set_option / dhqr_get_option):
+ *   "nb"          outer panel width, multiple of 32 in [32,128] (default 128)
+ *   "lookahead"   1 (default): panel chain on a high-priority stream ahead of the bulk update; 0: one stream, serial
+ *   "panel_fast"  1 (default): inner panels by CholeskyQR2 + Householder reconstruction with on-device fallback
+ *                 to the column-by-column kernel; 0: always column by column
+ *   "panel_ctas"  CTAs of the cooperative panel kernel (0 = default: 64 under look-ahead, one per SM otherwise)
+ *   "cvy_warps"   MMA warps per gemm_cvy CTA: 8 (default, 32x32 warp tiles) or 4 (64x32)
+ *   "sync"        1: cudaStreamSynchronize + error check after every kernel launch (debugging; implies serial)
+ *   "profile"     1: CUDA-event bracket per launch (implies serial), read with dhqr_profile_get
+ *   read-only:    "sms", "rank", "nranks", "panels_fast", "panels_fallback" (inner panels taken by either path)
+ *   experiment knobs kept for tools/: "panel_levels", "panel_backoff", "panel_trace", "la_trace", "vta_max_chunks",
+ *                 "hp_max_ctas", "hp_priority", "cvy_stagger" */
 int dhqr_set_option(dhqr_handle h, const char *key, int64_t value);
 int dhqr_get_option(dhqr_handle h, const char *key, int64_t *value);
 /* Number of kernel launches enqueued by this handle since creation (bench.py: gpu_launches). */
