@@ -126,6 +126,8 @@ struct dhqr_context {
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
     int cvy_warps = 8;
+    int tail_cols = 0;                                               // trailing width below which the chain is considered critical
+    int panel_ctas_hint = 0;                                            // set per panel by the look-ahead driver (0 = default)
     int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
@@ -369,7 +371,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
 // ------------------------------------------------------------------------------------------------
 static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P, int64_t ldp, int64_t mp, int ncols,
                         double* alpha, int voff, int64_t vtop, int64_t vrows) {
-    int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->lookahead ? 64 : c->sms);
+    int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->panel_ctas_hint > 0 ? c->panel_ctas_hint : (c->lookahead ? 64 : c->sms));
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
@@ -587,7 +589,12 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                         haveT = true;
                         cudaEventRecord(evNext[k], hp);                  // T'_k is in the ring: the bulk update may start
                     }
-                    if ((rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha))) break;
+                    // while the bulk update is wide the panel kernel leaves most SMs to it (64 CTAs); once the trailing
+                    // matrix is narrow the chain is the critical path and the panel takes every SM
+                    c->panel_ctas_hint = (lend - t1 >= c->tail_cols) ? 64 : c->sms;
+                    rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha);
+                    c->panel_ctas_hint = 0;
+                    if (rc) break;
                     if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
                 }
                 if ((rc = publish(k + 1))) break;
@@ -831,6 +838,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "cvy_warps")) {
         if (value != 4 && value != 8) return set_err(-3, "cvy_warps must be 4 or 8");
         c->cvy_warps = (int)value;
+    } else if (!strcmp(key, "tail_cols")) {
+        c->tail_cols = (int)value;
     } else if (!strcmp(key, "hp_priority")) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {

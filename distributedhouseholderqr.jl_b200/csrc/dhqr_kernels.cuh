@@ -656,8 +656,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     // CTA 0, one more exchange for its frozen rows, and a row-local triangular solve everywhere else.  In the
     // reference's storage: v_ij = W_ij^(j) / sqrt(U_jj) (i > j), v_jj = -S_j sqrt(U_jj), alpha_j = S_j Rt_jj,
     // R_ij = S_i Rt_ij.  Same reflectors as S:127-135 up to rounding (verified against the oracle), but it
-    // squares the panel's condition number on the way: if a Cholesky pivot is not positive or the factor's
-    // diagonal spans more than 1e5 the slab is reloaded and the column-by-column path below runs instead
+    // squares the panel's condition number on the way: if a Cholesky pivot is not positive, the first factor's
+    // diagonal spans more than 1e5, or Q1'Q1 is further than 1/4 from I (i.e. the second pass could not restore
+    // orthogonality to O(eps)), the slab is reloaded and the column-by-column path below runs instead
     // (that also reproduces the reference's NaN behaviour for zero columns).  The decision is taken from
     // identical data on every CTA, so it is grid-uniform without another exchange.
     // ============================================================================================
@@ -796,7 +797,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
             stamp(3);
             gram_exchange(1, ftag + 1);
             stamp(4);
-            chol(R2);
+            // CholeskyQR2 is as good as Householder QR iff the first pass left Q1 reasonably orthonormal:
+            // ||Q1'Q1 - I|| <= 1/4 bounds kappa(Q1) by 1.3 and the second pass restores orthogonality to O(eps).
+            for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                const int i = x / IB, j = x % IB;
+                if (!(fabs(Gm[i * LDG + j] - (i == j ? 1.0 : 0.0)) <= 0.25 / IB)) bad = 1;   // max-norm test, scaled for the 2-norm
+            }
+            __syncthreads();
+            if (!bad) chol(R2);
             stamp(5);
         }
         __syncthreads();

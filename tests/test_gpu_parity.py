@@ -293,6 +293,13 @@ def test_panel_fast_path_and_fallback(D, dev, oracle):
     assert h.get_option("panels_fallback") == b1 + 1
     assert oracle.qr_residual(Pi, np.asfortranarray(Hi), ai) < TOL_RES
     assert np.abs(ai - ar2).max() < 1e-6 * np.abs(ar2).max()          # alpha_7 is O(1e-9): relative accuracy limited by kappa
+    # moderately ill-conditioned (kappa ~ 1e6): whichever path the guards pick, the factorisation must be backward stable
+    Pm = P.copy()
+    Pm[:, 9] = Pm[:, 2] + 1e-6 * oracle.np_uniform(23, rows, 1)[:, 0]
+    Hm, am = run(Pm)
+    Hr3, ar3 = oracle.np_qr(Pm)
+    assert oracle.qr_residual(Pm, np.asfortranarray(Hm), am) < TOL_RES
+    assert np.abs(am - ar3).max() < 1e-8 * np.abs(ar3).max()
     # zero column: the reference gives f = Inf -> NaN (S:131); the fast path must not "fix" that
     Pz = P.copy()
     Pz[:, 5] = 0.0
