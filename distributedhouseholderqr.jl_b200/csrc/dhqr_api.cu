@@ -139,7 +139,6 @@ struct dhqr_context {
     cudaStream_t copy_stream = nullptr;      // compute stream of the _host_ entry points
     cudaStream_t d2h_stream = nullptr;       // drains finished panels to the host while the factorisation continues
     cudaStream_t h2d_stream = nullptr;       // uploads the right half while the left half is being factored
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> panel_events;
     // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
     double* mirror_host = nullptr;
@@ -763,8 +762,6 @@ static int create_common(dhqr_handle* h, int device) {
         CU(cudaStreamCreateWithPriority(&c->hp_lo, cudaStreamNonBlocking, lo));
         c->hp_stream = c->hp_hi;
     }
-    CU(cudaEventCreateWithFlags(&c->ev0, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev1, cudaEventDisableTiming));
     *h = c;
     return 0;
 }
@@ -814,8 +811,6 @@ int dhqr_destroy(dhqr_handle c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
     return 0;
 }
