@@ -127,6 +127,8 @@ struct dhqr_context {
     int cvy_stagger = 0;
     int cvy_warps = 8;
     int tail_cols = 0;                                               // trailing width below which the chain is considered critical
+    int wide_panel_ctas = 64;                                           // panel CTAs while the bulk update is wide
+    bool bulk_wide = true;                                              // set per step by the look-ahead driver
     int panel_ctas_hint = 0;                                            // set per panel by the look-ahead driver (0 = default)
     int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
@@ -314,7 +316,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     const int tiles = (next + bn - 1) / bn;
     const int nchunks = (int)((rows + KC1 - 1) / KC1);
     const int nsplit = pick_splits(tiles, nchunks, c->sms, max_chunks, (int64_t)(w.wpart_elems / ((size_t)bn * NBPK)),
-                                   (st == c->hp_stream && c->lookahead) ? c->hp_max_ctas : 0);
+                                   (st == c->hp_stream && c->lookahead && c->bulk_wide) ? c->hp_max_ctas : 0);
     const int64_t pstride = (int64_t)tiles * bn * NBPK;
     if ((size_t)(pstride * nsplit) > w.wpart_elems) return set_err(4001, "internal: W partial workspace too small");
     if ((size_t)next * NBPK > w.wsum_elems) return set_err(4003, "internal: W workspace too small");
@@ -576,6 +578,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             const int64_t t1 = k + 1 < K ? panels[k + 1].c + panels[k + 1].kb : t0;      // end of panel k+1
             const int64_t t2 = k + 2 < K ? panels[k + 2].c + panels[k + 2].kb : t1;      // end of panel k+2
             int64_t lo, hi;
+            c->bulk_wide = (c->tail_cols <= 0) || (lend - t1 >= c->tail_cols);   // bulk-bound (wide) vs chain-bound (narrow) phase
             double* lk = c->linv_ring[k % 3];
             bool haveT = false;                                          // T'_k in lk (this rank)
             if (k + 1 < K) {
@@ -590,7 +593,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                     }
                     // while the bulk update is wide the panel kernel leaves most SMs to it (64 CTAs); once the trailing
                     // matrix is narrow the chain is the critical path and the panel takes every SM
-                    c->panel_ctas_hint = (lend - t1 >= c->tail_cols) ? 64 : c->sms;
+                    c->panel_ctas_hint = c->bulk_wide ? c->wide_panel_ctas : (c->tail_cols > 0 ? c->sms : c->wide_panel_ctas);
                     rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha);
                     c->panel_ctas_hint = 0;
                     if (rc) break;
@@ -617,6 +620,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             cudaEventRecord(evBulk[k], st);
         }
         if (rc) break;
+        c->bulk_wide = true;
         cudaStreamWaitEvent(st, evPanel[K - 1], 0);                // join: alpha and the last panel come from hp
         if (c->la_trace) {
             cudaStreamSynchronize(st);
@@ -833,6 +837,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "cvy_warps")) {
         if (value != 4 && value != 8) return set_err(-3, "cvy_warps must be 4 or 8");
         c->cvy_warps = (int)value;
+    } else if (!strcmp(key, "wide_panel_ctas")) {
+        c->wide_panel_ctas = (int)value;
     } else if (!strcmp(key, "tail_cols")) {
         c->tail_cols = (int)value;
     } else if (!strcmp(key, "hp_priority")) {

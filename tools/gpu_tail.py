@@ -14,6 +14,9 @@ def timeit(reps=3):
         e0.record(); D.householder_(A, al, 0); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for tc in (0, 768, 1280, 1792, 2304):
-    h.set_option("tail_cols", tc)
-    t = timeit(); print(f"tail_cols={tc}: {t:.2f} ms  {fl / t / 1e9:.2f} TFLOP/s", flush=True)
+base = {"tail_cols": 0, "hp_max_ctas": 0, "wide_panel_ctas": 64}
+for opts in ({}, {"tail_cols": 1536, "hp_max_ctas": 48}, {"tail_cols": 1536, "hp_max_ctas": 32}, {"tail_cols": 1536, "hp_max_ctas": 48, "wide_panel_ctas": 48},
+             {"tail_cols": 2048, "hp_max_ctas": 48}, {"tail_cols": 2048, "hp_max_ctas": 64, "wide_panel_ctas": 48}, {"tail_cols": 1024, "hp_max_ctas": 48},
+             {"tail_cols": 1536, "hp_max_ctas": 0, "wide_panel_ctas": 48}):
+    for k, v in {**base, **opts}.items(): h.set_option(k, v)
+    t = timeit(); print(f"{opts}: {t:.2f} ms  {fl / t / 1e9:.2f} TFLOP/s", flush=True)
