@@ -84,16 +84,18 @@ def cpu_sample(m, n, target_s=12.0, jstop=None):
     A = co.fill_uniform(0, m, n)
     if jstop is None:
         best = None
-        for nt in sorted({cores, max(1, cores // 2)}, reverse=True):   # calibration: 4 column steps per thread count
+        for nt in sorted({cores, max(1, cores // 2)}, reverse=True):   # calibration: 16 column steps per thread count
+            co.qr_steps(A, 2, nt)                                       # (2 untimed steps first: thread start-up, page touch)
+            A = co.fill_uniform(0, m, n)
             t = time.perf_counter()
-            co.qr_steps(A, 4, nt)
+            co.qr_steps(A, 16, nt)
             dt = max(time.perf_counter() - t, 1e-4)
             if best is None or dt < best[0]:
                 best = (dt, nt)
             A = co.fill_uniform(0, m, n)
         dt, cores = best
         os.environ["DHQR_CPU_THREADS"] = str(cores)
-        jstop = int(max(8, min(n, 4 * target_s / dt)))
+        jstop = int(max(8, min(n, 16 * target_s / dt)))
     t = time.perf_counter()
     _, fl = co.qr_steps(A, jstop, cores)
     dt = time.perf_counter() - t
