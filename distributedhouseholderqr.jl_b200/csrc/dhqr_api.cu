@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -376,12 +377,12 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
     rpc = rup(rpc, 8);
-    while ((size_t)IB * ((size_t)rpc | 1) * 8 > 184 * 1024 && gmax < std::min(c->sms, PANEL_MAXG)) {   // slab too big: use more CTAs
+    while ((size_t)IB * ((size_t)rpc + 4) * 8 > 184 * 1024 && gmax < std::min(c->sms, PANEL_MAXG)) {   // slab too big: use more CTAs
         gmax = std::min(gmax * 2, std::min(c->sms, PANEL_MAXG));
         rpc = rup(std::max<int64_t>((mp + gmax - 1) / gmax, 64), 8);
     }
     const int G = (int)((mp + rpc - 1) / rpc);
-    const int lds = (int)rpc | 1;
+    const int lds = (int)rpc + 4;   // rpc is a multiple of 8 -> lds == 4 mod 8
     const size_t smem = (size_t)IB * lds * 8;
     if (smem > 184 * 1024) return set_err(-2, "m too large for the resident panel kernel (%lld rows per CTA)", (long long)rpc);
     if (c->ll_epoch > 0xF0000000u) {   // tag space nearly used up: start over with clean cells
@@ -882,6 +883,7 @@ int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
     else if (!strcmp(key, "profile")) *value = c->profile;
     else if (!strcmp(key, "lookahead")) *value = c->lookahead;
     else if (!strcmp(key, "panel_fast")) *value = c->panel_fast;
+    else if (!strcmp(key, "panel_variant")) *value = PANEL_VARIANT;
     else if (!strcmp(key, "panels_fast") || !strcmp(key, "panels_fallback")) {
         int st2[2] = {0, 0};
         if (c->fast_stats) CU(cudaMemcpy(st2, c->fast_stats, sizeof(st2), cudaMemcpyDeviceToHost));

@@ -19,6 +19,10 @@ constexpr int KC = 32;        // K-chunk: rows per stage in gemm_vta, V columns 
 constexpr int LDK = KC + 4;   // padded leading dim of [column][k] smem tiles: 36 doubles (288 B), 36 % 16 == 4
 constexpr int IB = 32;        // inner (cooperative) panel width
 constexpr int PANEL_THREADS = 512;
+#ifndef DHQR_PANEL_VARIANT
+#define DHQR_PANEL_VARIANT 4   // bit 2: triangular solves of the panel fast path on the fp64 tensor pipe (0: row-by-row
+#endif                         // substitution on the vector pipe); A/B results in profiles/r01_panel_variants.txt
+constexpr int PANEL_VARIANT = DHQR_PANEL_VARIANT;
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier, TMA bulk copy, fp64 tensor-core MMA
@@ -590,7 +594,7 @@ struct PanelArgs {
     int64_t vtop;         // window rows above the panel top (zero-filled in vpk)
     int64_t vrows;        // total window rows incl. padding (zero-filled below vtop+mp)
     int rows_per_cta;
-    int lds;              // slab leading dimension (>= rows_per_cta, odd)
+    int lds;              // slab leading dimension (>= rows_per_cta rounded up to 4, == 4 mod 8: conflict-free DMMA fragments)
     unsigned long long* cells;   // [IB steps][(G + 2) * IB cells][2 words]
     uint32_t epoch;       // tags epoch+1 .. epoch+IB belong to this launch
     int backoff;          // ns to sleep between polls of a cell that is not there yet (0 = spin)
@@ -643,9 +647,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     auto vcell = [&](int step, int c) { return a.cells + (size_t)step * step_words + ((size_t)G * IB + IB + c) * 2; };
     auto clampi = [&](int64_t x) { return x < 0 ? 0 : (x > nr ? nr : (int)x); };
 
-    // load slab (coalesced along rows)
+    // load slab (coalesced along rows); rows [nr, nr4) are zero so that the DMMAs can run on 8-row tiles
+    const int nr4 = (nr + 7) & ~7;
     for (int c = warp; c < nc; c += PNW)
-        for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
+        for (int r = lane; r < nr4; r += 32) S[c * lds + r] = r < nr ? a.P[(int64_t)c * a.ldp + row0 + r] : 0.0;
     __syncthreads();
 
     // ============================================================================================
@@ -666,8 +671,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     if (a.fast && nc == IB && a.mp >= 2 * IB && a.rows_per_cta >= IB) {
         constexpr int NGP = IB * (IB + 1) / 2;   // 528 pairs (i >= j)
         constexpr int LDG = IB + 1;
-        __shared__ double Gm[IB * LDG], R1[IB * LDG], R2[IB * LDG], Wt[IB * LDG];
+        __shared__ double Gm[IB * LDG], Wt[IB * LDG];
+        __shared__ __align__(16) double R1[IB * IB], R2[IB * IB];   // Cholesky factors, rows 16-byte aligned (paired loads)
         __shared__ double rinv[IB], Sg[IB], Ud[IB], rsq[IB], cl[IB];
+        __shared__ double Dv[4 * 64], Wn[6 * 64];   // DMMA triangular solve: inverses of the 8x8 diagonal blocks, -R_ab * inv(R_bb)
         __shared__ int bad;
         const size_t reg = (size_t)(G + 1) * NGP;
         auto c2p = [&](int e, int g, int t) { return a.cells2 + ((size_t)e * reg + (size_t)g * NGP + t) * 2; };
@@ -677,43 +684,50 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
 
         // Gram matrix of the slab -> all-CTA sum in Gm (both triangles); partials summed in CTA order
         auto gram_exchange = [&](int e, uint32_t tag) {
-            // partial Gram of the slab with 2x2 register tiles: 136 tiles (lower triangle of the 16x16 tile grid)
-            // x 3 interleaved row groups = 408 threads; the 3 partials of an entry are then added in fixed order
+            // partial Gram of the slab on the fp64 tensor pipe: the lower 16x16 tiles (0,0), (1,0), (1,1) of S'S, each
+            // by NKG warps that split the slab's 4-row steps; the NKG partials of a tile are added into Gm in group
+            // order (fixed -> deterministic).  Both fragments of a DMMA are slab columns, k = slab rows ("TN" like gemm_vta).
             {
-                constexpr int NT = 136;
-                const int grp = tid / NT, blk = tid % NT;
-                double* Gp = grp == 0 ? Gm : (grp == 1 ? R2 : Wt);     // free scratch at this point (R1 must survive pass 2)
-                if (grp < 3) {
-                    int I = 0;
-                    while ((I + 1) * (I + 2) / 2 <= blk) ++I;
-                    const int J = blk - I * (I + 1) / 2;
-                    const double* a0 = S + (2 * I) * lds;
-                    const double* a1 = a0 + lds;
-                    const double* b0 = S + (2 * J) * lds;
-                    const double* b1 = b0 + lds;
-                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-                    int r = grp;
-                    for (; r + 9 < nr; r += 12) {   // 4 rows in flight per iteration (LDS latency), fixed summation order
-                        double x0[4], x1[4], y0[4], y1[4];
+                constexpr int NKG = 5;
+                const int tile = warp % 3, kg = warp / 3;
+                const int ti = tile == 0 ? 0 : 1, tj = tile == 2 ? 1 : 0;
+                double acc[2][2][2];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { x0[u] = a0[r + 3 * u]; x1[u] = a1[r + 3 * u]; y0[u] = b0[r + 3 * u]; y1[u] = b1[r + 3 * u]; }
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { c00 += x0[u] * y0[u]; c01 += x0[u] * y1[u]; c10 += x1[u] * y0[u]; c11 += x1[u] * y1[u]; }
+                    for (int v = 0; v < 2; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+                if (warp < 3 * NKG) {
+                    const int ks = nr4 >> 2;
+                    const int k_lo = (ks * kg) / NKG, k_hi = (ks * (kg + 1)) / NKG;
+                    const double* pa = S + (ti * 16 + (lane >> 2)) * lds + (lane & 3);
+                    const double* pb = S + (tj * 16 + (lane >> 2)) * lds + (lane & 3);
+#pragma unroll 2
+                    for (int k = k_lo; k < k_hi; ++k) {
+                        const double a0 = pa[4 * k], a1 = pa[8 * lds + 4 * k];
+                        const double b0 = pb[4 * k], b1 = pb[8 * lds + 4 * k];
+                        dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+                        dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+                        dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+                        dmma(acc[1][1][0], acc[1][1][1], a1, b1);
                     }
-                    for (; r < nr; r += 3) {
-                        const double x0 = a0[r], x1 = a1[r], y0 = b0[r], y1 = b1[r];
-                        c00 += x0 * y0; c01 += x0 * y1; c10 += x1 * y0; c11 += x1 * y1;
-                    }
-                    Gp[(2 * I) * LDG + 2 * J] = c00;
-                    Gp[(2 * I) * LDG + 2 * J + 1] = c01;
-                    Gp[(2 * I + 1) * LDG + 2 * J] = c10;
-                    Gp[(2 * I + 1) * LDG + 2 * J + 1] = c11;
                 }
-                __syncthreads();
+                for (int g = 0; g < NKG; ++g) {
+                    if (warp < 3 * NKG && kg == g) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                double* o = Gm + (ti * 16 + u * 8 + (lane >> 2)) * LDG + tj * 16 + v * 8 + 2 * (lane & 3);
+                                if (g == 0) { o[0] = acc[u][v][0]; o[1] = acc[u][v][1]; }
+                                else { o[0] += acc[u][v][0]; o[1] += acc[u][v][1]; }
+                            }
+                    }
+                    __syncthreads();
+                }
                 for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
                     const int i = x / IB, j = x % IB;
                     if (j > i) continue;
-                    ll_store(c2p(e, cta, i * (i + 1) / 2 + j), (Gm[i * LDG + j] + R2[i * LDG + j]) + Wt[i * LDG + j], tag);
+                    ll_store(c2p(e, cta, i * (i + 1) / 2 + j), Gm[i * LDG + j], tag);
                 }
             }
             for (int q = warp; cta + q * G < NGP; q += PNW) {   // owner of pair t = cta + q G
@@ -729,34 +743,154 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                 sum = warp_sum(sum);
                 if (lane == 0) ll_store(c2t(e, t), sum, tag);
             }
-            for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
-                const int i = x / IB, j = x % IB;
-                if (j > i) continue;
-                const double v = ll_wait(c2t(e, i * (i + 1) / 2 + j), tag, a.backoff);
-                Gm[i * LDG + j] = v;
-                Gm[j * LDG + i] = v;
+            {   // totals: both cells of a thread are requested before either is waited for (one L2 round trip, not two)
+                static_assert(IB * IB == 2 * PANEL_THREADS, "two cells per thread");
+                unsigned long long w0[2], w1[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int x = tid + u * PANEL_THREADS, i = x / IB, j = x % IB;
+                    if (j <= i) ll_peek(c2t(e, i * (i + 1) / 2 + j), w0[u], w1[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int x = tid + u * PANEL_THREADS, i = x / IB, j = x % IB;
+                    if (j <= i) {
+                        const double v = ll_finish(c2t(e, i * (i + 1) / 2 + j), w0[u], w1[u], tag, a.backoff);
+                        Gm[i * LDG + j] = v;
+                        Gm[j * LDG + i] = v;
+                    }
+                }
             }
             __syncthreads();
         };
-        // upper Cholesky factor of Gm -> Rout, 1/diag -> rinv; flags a non-positive / non-finite pivot
+        // x[j+1 ..] -= q * Rrow[j+1 ..] with paired (16-byte) broadcast loads; every condition folds once j is unrolled
+#define DHQR_ROW_AXPY(x, q, Rrow, j)                                                          \
+        _Pragma("unroll") for (int k_ = 0; k_ < IB; k_ += 2) {                                \
+            if (k_ > (j)) {                                                                   \
+                const double2 rr_ = *reinterpret_cast<const double2*>((Rrow) + k_);           \
+                x[k_] -= (q) * rr_.x;                                                         \
+                x[k_ + 1] -= (q) * rr_.y;                                                     \
+            } else if (k_ == (j)) {                                                           \
+                x[k_ + 1] -= (q) * (Rrow)[k_ + 1];                                            \
+            }                                                                                 \
+        }
+        // rsqrt(double) without the library's slow-path branch (keeps the step a single basic block the scheduler can interleave
+        // with the rank-1 updates): MUFU seed + one cubic step, same operations as the fast path of rsqrt()
+        auto rsqrt_nb = [](double d) {
+            double y0;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            const double t = y0 * y0;
+            const double e = fma(d, -t, 1.0);
+            const double pq = fma(e, 0.375, 0.5);
+            const double q = y0 * e;
+            return fma(pq, q, y0);
+        };
+        // upper Cholesky factor of Gm -> Rout ([IB][IB], zero below the diagonal), 1/diag -> rinv; flags a non-positive /
+        // non-finite pivot.  One warp, column `lane` of the trailing matrix in registers, row j broadcast through Rout: a step
+        // is a dependent chain (rsqrt -> scale -> update of the next pivot), so more threads would only add barriers.
+        // Software-pipelined: the next pivot is updated first and its rsqrt is issued before the remaining rank-1 updates
+        // of the step, so that the one warp's in-order issue overlaps the two.
         auto chol = [&](double* Rout) {
-            for (int x = tid; x < IB * LDG; x += PANEL_THREADS) Rout[x] = 0.0;
-            __syncthreads();
-            for (int j = 0; j < IB; ++j) {
-                const double d = Gm[j * LDG + j];
-                const double ri = rsqrt(d);
-                if (tid == 0) {
-                    if (!(d > 0.0) || !(d < 1e300)) bad = 1;
-                    rinv[j] = ri;
-                    Rout[j * LDG + j] = d * ri;
+            if (warp == 0) {
+                double g[IB];
+#pragma unroll
+                for (int i = 0; i < IB; ++i) g[i] = Gm[i * LDG + lane];
+                double d = __shfl_sync(0xffffffffu, g[0], 0);
+                double ri = rsqrt_nb(d);
+#pragma unroll
+                for (int j = 0; j < IB; ++j) {
+                    if (lane == 0) {
+                        if (!(d > 0.0) || !(d < 1e300)) bad = 1;
+                        rinv[j] = ri;
+                    }
+                    const double r = lane == j ? d * ri : g[j] * ri;   // R(j, lane)
+                    Rout[j * IB + lane] = lane >= j ? r : 0.0;
+                    double dn = 1.0, rin = 1.0;
+                    if (j + 1 < IB) {
+                        const double rj1 = __shfl_sync(0xffffffffu, r, j + 1);
+                        if (j + 1 <= lane) g[j + 1] -= rj1 * r;
+                        dn = __shfl_sync(0xffffffffu, g[j + 1], j + 1);
+                        rin = rsqrt_nb(dn);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = j + 2; i < IB; ++i) {
+                        const double rji = Rout[j * IB + i];            // broadcast
+                        if (i <= lane) g[i] -= rji * r;
+                    }
+                    d = dn;
+                    ri = rin;
                 }
-                for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
-                    const int i = x / IB, k = x % IB;
-                    if (i == j && k > j) Rout[j * LDG + k] = Gm[j * LDG + k] * ri;
-                    else if (i > j && k >= i) Gm[i * LDG + k] -= (Gm[j * LDG + i] * ri) * (Gm[j * LDG + k] * ri);
-                }
-                __syncthreads();
             }
+            __syncthreads();
+        };
+        // Triangular solve on the fp64 tensor pipe: slab rows [8 tile_lo, nr) <- rows * Rm^{-1}, Rm upper triangular ([IB][IB]),
+        // dgi = 1 / diag(Rm).  Blocked by 8 columns: X'_b = X_b inv(R_bb) - sum_{a<b} X'_a (R_ab inv(R_bb)); the 8x8 diagonal
+        // inverses and the 6 products are formed once per call (Dv, Wn), the B fragments live in registers, and one warp
+        // owns an 8-row tile (A fragments = slab columns, the finished block goes back through the slab to change layout).
+        // The substitution above is bound by the shared-memory -> register bandwidth of its 496 broadcast operands per row.
+        auto trsm_dmma = [&](const double* Rm, const double* dgi, int tile_lo) {
+            if (tid < 32) {
+                const int b = tid >> 3, c = tid & 7;
+                const double* Rb = Rm + (8 * b) * IB + 8 * b;
+                double inv[8];
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {
+                    double sacc = i == c ? 1.0 : 0.0;
+#pragma unroll
+                    for (int j = i + 1; j < 8; ++j) sacc -= Rb[i * IB + j] * inv[j];
+                    inv[i] = i <= c ? sacc * dgi[8 * b + i] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Dv[b * 64 + i * 8 + c] = inv[i];
+            }
+            __syncthreads();
+            if (tid < 6 * 64) {
+                const int pr = tid >> 6, i = (tid >> 3) & 7, j = tid & 7;
+                const int ba = pr < 3 ? 0 : (pr < 5 ? 1 : 2), bb = pr < 3 ? pr + 1 : (pr < 5 ? pr - 1 : 3);
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sacc += Rm[(8 * ba + i) * IB + 8 * bb + k] * Dv[bb * 64 + k * 8 + j];
+                Wn[pr * 64 + i * 8 + j] = -sacc;
+            }
+            __syncthreads();
+            double bd[4][2], bw[6][2];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) bd[b][h] = Dv[b * 64 + (4 * h + (lane & 3)) * 8 + (lane >> 2)];
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) bw[pr][h] = Wn[pr * 64 + (4 * h + (lane & 3)) * 8 + (lane >> 2)];
+            const int ntiles = nr4 >> 3;
+            for (int tile = tile_lo + warp; tile < ntiles; tile += PNW) {
+                const double* pa = S + (lane & 3) * lds + tile * 8 + (lane >> 2);
+                double* pc = S + (2 * (lane & 3)) * lds + tile * 8 + (lane >> 2);
+                double xa[3][2];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double o0 = pa[(8 * b) * lds], o1 = pa[(8 * b + 4) * lds];
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma(c0, c1, o0, bd[b][0]);
+                    dmma(c0, c1, o1, bd[b][1]);
+#pragma unroll
+                    for (int a2 = 0; a2 < b; ++a2) {
+                        const int pr = a2 == 0 ? b - 1 : (a2 == 1 ? b + 1 : 5);   // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+                        dmma(c0, c1, xa[a2][0], bw[pr][0]);
+                        dmma(c0, c1, xa[a2][1], bw[pr][1]);
+                    }
+                    __syncwarp();   // every lane has read X_b in the A layout before it is overwritten in the C layout
+                    pc[(8 * b) * lds] = c0;
+                    pc[(8 * b + 1) * lds] = c1;
+                    if (b < 3) {
+                        __syncwarp();
+                        xa[b][0] = pa[(8 * b) * lds];
+                        xa[b][1] = pa[(8 * b + 4) * lds];
+                    }
+                }
+            }
+            __syncthreads();
         };
         // slab <- slab * R^{-1}  (row-local forward substitution; one row per thread)
         auto trsm = [&](const double* R) {
@@ -768,9 +902,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                 for (int j = 0; j < IB; ++j) {
                     const double q = x[j] * rinv[j];
                     x[j] = q;
-#pragma unroll
-                    for (int k = j + 1; k < IB; ++k) x[k] -= q * R[j * LDG + k];
-                    asm volatile("" ::: "memory");   // keeps ptxas from hoisting all 496 LDS (it spills 4 KB/thread otherwise)
+                    DHQR_ROW_AXPY(x, q, R + j * IB, j)
+                    asm volatile("" ::: "memory");   // keeps ptxas from hoisting all the LDS (it spills 4 KB/thread otherwise)
                 }
 #pragma unroll
                 for (int k = 0; k < IB; ++k) S[k * lds + r] = x[k];
@@ -788,12 +921,12 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         stamp(2);
         if (tid == 0 && !bad) {   // conditioning guard on the first factor
             double dmin = R1[0], dmax = R1[0];
-            for (int j = 1; j < IB; ++j) { dmin = fmin(dmin, R1[j * LDG + j]); dmax = fmax(dmax, R1[j * LDG + j]); }
+            for (int j = 1; j < IB; ++j) { dmin = fmin(dmin, R1[j * IB + j]); dmax = fmax(dmax, R1[j * IB + j]); }
             if (!(dmin > 1e-5 * dmax)) bad = 1;
         }
         __syncthreads();
         if (!bad) {
-            trsm(R1);
+            if (PANEL_VARIANT & 4) trsm_dmma(R1, rinv, 0); else trsm(R1);
             stamp(3);
             gram_exchange(1, ftag + 1);
             stamp(4);
@@ -809,18 +942,22 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         }
         __syncthreads();
         if (!bad) {
-            trsm(R2);
+            if (PANEL_VARIANT & 4) trsm_dmma(R2, rinv, 0); else trsm(R2);
             stamp(6);
             // Rt = R2 * R1 (upper) -> Gm
             for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
                 const int i = x / IB, k = x % IB;
                 double sacc = 0.0;
                 if (k >= i)
-                    for (int j = i; j <= k; ++j) sacc += R2[i * LDG + j] * R1[j * LDG + k];
+                    for (int j = i; j <= k; ++j) sacc += R2[i * IB + j] * R1[j * IB + k];
                 Gm[i * LDG + k] = sacc;
             }
+            __syncthreads();      // R2 is free from here: it becomes Up, the frozen rows U(j, j+1:) with aligned rows
+            double* Up = R2;
             if (cta == 0) {
-                // LU of the top block of E - Q S on CTA 0: Wt(i,k) = Q(i,k); row j is frozen at step j
+                // LU of the top block of E - Q S on CTA 0: Wt(i,k) = Q(i,k); row j is frozen at step j.  Block-wide with a
+                // barrier per step: a one-warp register version (shuffles) was 2x slower, and pre-computing the next pivot
+                // to take the division off the chain gained nothing (profiles/r01_panel_variants.txt).
                 for (int x = tid; x < IB * IB; x += PANEL_THREADS) Wt[(x / IB) * LDG + (x % IB)] = S[(x % IB) * lds + (x / IB)];
                 __syncthreads();
                 for (int j = 0; j < IB; ++j) {
@@ -836,18 +973,41 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                     __syncthreads();
                 }
                 for (int x = tid; x < IB * IB; x += PANEL_THREADS)
-                    if (x % IB > x / IB) ll_store(c2u(x), Wt[(x / IB) * LDG + (x % IB)], ftag + 2);
+                    if (x % IB > x / IB) { const double v = Wt[(x / IB) * LDG + (x % IB)]; ll_store(c2u(x), v, ftag + 2); Up[x] = v; }
                 if (tid < IB) { ll_store(c2u(IB * IB + tid), Ud[tid], ftag + 2); ll_store(c2u(IB * IB + IB + tid), Sg[tid], ftag + 2); }
             } else {
-                for (int x = tid; x < IB * IB; x += PANEL_THREADS)
-                    if (x % IB > x / IB) Wt[(x / IB) * LDG + (x % IB)] = ll_wait(c2u(x), ftag + 2, a.backoff);
-                if (tid < IB) { Ud[tid] = ll_wait(c2u(IB * IB + tid), ftag + 2, a.backoff); Sg[tid] = ll_wait(c2u(IB * IB + IB + tid), ftag + 2, a.backoff); }
+                {   // all cells of a thread requested before the first wait
+                    unsigned long long w0[4], w1[4];
+                    const int xs[4] = {tid, tid + PANEL_THREADS, IB * IB + tid, IB * IB + IB + tid};
+                    const bool on[4] = {tid % IB > tid / IB, (tid + PANEL_THREADS) % IB > (tid + PANEL_THREADS) / IB, tid < IB, tid < IB};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (on[u]) ll_peek(c2u(xs[u]), w0[u], w1[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!on[u]) continue;
+                        const double v = ll_finish(c2u(xs[u]), w0[u], w1[u], ftag + 2, a.backoff);
+                        if (u < 2) Up[xs[u]] = v;
+                        else if (u == 2) Ud[tid] = v;
+                        else Sg[tid] = v;
+                    }
+                }
             }
             __syncthreads();
             stamp(7);
             if (tid < IB) { rsq[tid] = 1.0 / sqrt(Ud[tid]); cl[tid] = -Sg[tid] / Ud[tid]; }
             __syncthreads();
             // rows below the top block: L2 = M2 U^{-1}, scaled to the reference's |v|^2 = 2 convention
+            if (PANEL_VARIANT & 4) {
+                // the same recurrence as a triangular solve V = M Rr^{-1}, Rr = diag(sqrt(Ud)) (I + diag(cl) striu(U)), in R1
+                for (int x = tid; x < IB * IB; x += PANEL_THREADS) {
+                    const int i = x / IB, k = x % IB;
+                    const double sq = Ud[i] * rsq[i];
+                    R1[x] = k > i ? (cl[i] * Up[x]) * sq : (k == i ? sq : 0.0);
+                }
+                __syncthreads();
+                trsm_dmma(R1, rsq, cta == 0 ? IB / 8 : 0);
+            } else
             for (int r = tid; r < nr; r += PANEL_THREADS) {
                 if (row0 + r < IB) continue;
                 double x[IB];
@@ -858,8 +1018,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                     const double wj = x[j];
                     const double l = wj * cl[j];
                     x[j] = wj * rsq[j];
-#pragma unroll
-                    for (int k = j + 1; k < IB; ++k) x[k] -= l * Wt[j * LDG + k];
+                    DHQR_ROW_AXPY(x, l, Up + j * IB, j)
                     asm volatile("" ::: "memory");
                 }
 #pragma unroll
@@ -882,7 +1041,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
             // fall back: the slab was modified by the first TRSM at most; reload the untouched panel from memory
             __syncthreads();
             for (int c = warp; c < nc; c += PNW)
-                for (int r = lane; r < nr; r += 32) S[c * lds + r] = a.P[(int64_t)c * a.ldp + row0 + r];
+                for (int r = lane; r < nr4; r += 32) S[c * lds + r] = r < nr ? a.P[(int64_t)c * a.ldp + row0 + r] : 0.0;
         }
         __syncthreads();
         if (a.fast_stats && cta == 0 && tid == 0) atomicAdd(&a.fast_stats[done ? 0 : 1], 1);

@@ -63,7 +63,8 @@ int dhqr_destroy(dhqr_handle h);
  *   "cvy_warps"   MMA warps per gemm_cvy CTA: 8 (default, 32x32 warp tiles) or 4 (64x32)
  *   "sync"        1: cudaStreamSynchronize + error check after every kernel launch (debugging; implies serial)
  *   "profile"     1: CUDA-event bracket per launch (implies serial), read with dhqr_profile_get
- *   read-only:    "sms", "rank", "nranks", "panels_fast", "panels_fallback" (inner panels taken by either path)
+ *   read-only:    "sms", "rank", "nranks", "panels_fast", "panels_fallback" (inner panels taken by either path),
+ *                 "panel_variant" (compile-time DHQR_PANEL_VARIANT of the panel kernel's fast path)
  *   experiment knobs kept for tools/: "panel_levels", "panel_backoff", "panel_trace", "la_trace", "vta_max_chunks",
  *                 "hp_max_ctas", "hp_priority", "cvy_stagger" */
 int dhqr_set_option(dhqr_handle h, const char *key, int64_t value);
