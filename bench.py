@@ -84,12 +84,12 @@ def cpu_sample(m, n, target_s=12.0, jstop=None):
     A = co.fill_uniform(0, m, n)
     if jstop is None:
         best = None
-        for nt in sorted({cores, max(1, cores // 2)}, reverse=True):   # calibration: 16 column steps per thread count
-            co.qr_steps(A, 2, nt)                                       # (2 untimed steps first: thread start-up, page touch)
-            A = co.fill_uniform(0, m, n)
+        for nt in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):   # calibration: 32 column steps per
+            co.qr_steps(A, 2, nt)                                       # thread count (2 untimed steps first: thread start-up,
+            A = co.fill_uniform(0, m, n)                                # page touch); all / half / a quarter of the host threads
             t = time.perf_counter()
-            co.qr_steps(A, 16, nt)
-            dt = max(time.perf_counter() - t, 1e-4)
+            co.qr_steps(A, 32, nt)
+            dt = max(time.perf_counter() - t, 1e-4) / 2.0
             if best is None or dt < best[0]:
                 best = (dt, nt)
             A = co.fill_uniform(0, m, n)
