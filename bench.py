@@ -216,9 +216,18 @@ def run_ours(args):
     launches_all = int(sumover(float(launches)))
 
     # parity of the last timed factorisation: ||QR - A||_F / ||A||_F (single GPU; multi-GPU checked in tests)
-    resid = None
+    resid, colnorm = None, None
     if world == 1 and not args.no_check:
         resid = gpu_residual(torch, D, pool[(K - 1) % pool_n], alpha, m, n, dev)
+    if not args.no_check:
+        # size-independent and rank-local: Q orthogonal => ||A0[:, j]|| == ||R[0:j+1, j]|| for every column of the block
+        try:
+            A0 = D.colmajor_empty(m, nl, dev)
+            D.fill_uniform_(A0, 0, 0, c0, h)
+            colnorm = maxover(column_norm_defect(torch, pool[(K - 1) % pool_n], alpha, A0, n, c0))
+            del A0
+        except Exception as e:   # a failing check must not take the timing line with it
+            colnorm = f"check failed: {type(e).__name__}: {e}"
 
     # ---- per-kernel-class profile (separate, untimed step) -> roofline of the dominant kernel ----
     h.set_option("profile", 1)
@@ -295,11 +304,22 @@ def run_ours(args):
                           "m": m, "n": n, "nb": nb or 128, "cols_per_gpu": nl, "l2": "inputs (m*n*8 B per step) larger than L2; fresh matrix per step",
                           "timing": "CUDA events around K back-to-back qr! calls on fresh matrices, max over ranks"},
                "clocks": clocks, "gpu_launches": launches_all, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-               "parity": {"qr_residual_fro_rel": resid, "tolerance": 1e-13}}
+               "parity": {"qr_residual_fro_rel": resid, "tolerance": 1e-13,
+                          "column_norm_defect_max_rel": colnorm, "column_norm_tolerance": 1e-12}}
         print(json.dumps(out))
     if world > 1:
         D.shutdown_distributed()
         dist.destroy_process_group()
+
+
+def column_norm_defect(torch, H, alpha, A0, n, c0):
+    """max_j | ||R[0:j+1, j]|| / ||A0[:, j]|| - 1 | over the columns of one column block (H = factored block, global
+    columns c0..; R's strict upper part sits above the global diagonal, diag(R) in alpha)."""
+    nl = H.shape[1]
+    U = torch.triu(H[:n], diagonal=1 - c0)          # keeps (i, j) with i < c0 + j
+    r2 = (U * U).sum(0) + alpha[c0:c0 + nl] ** 2
+    a2 = (A0 * A0).sum(0)
+    return float((torch.sqrt(r2 / a2) - 1.0).abs().max().item())
 
 
 def gpu_residual(torch, D, A, alpha, m, n, dev):

@@ -44,3 +44,22 @@ def test_rejects_row_major_and_wrong_dtype():
         _lda(torch.zeros(4, 3, dtype=torch.float64))            # row-major
     with pytest.raises(TypeError):
         _lda(D.colmajor_empty(4, 3, device="cpu").float())
+
+
+def test_bench_column_norm_property_on_oracle_output():
+    """bench.py's rank-local parity property (||R[0:j+1, j]|| == ||A0[:, j]||) holds for the oracle's factorisation of any
+    column block and trips on a corrupted one."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "oracle"))
+    import bench, dhqr_oracle as O
+    co = O.COracle()
+    m, n = 200, 64
+    A0 = co.fill_uniform(3, m, n)
+    H, alpha = co.qr(A0.copy(order="F"))
+    for c0, nl in ((0, 64), (0, 24), (24, 40)):
+        blk = lambda X: torch.from_numpy(np.ascontiguousarray(X[:, c0:c0 + nl]))
+        assert bench.column_norm_defect(torch, blk(H), torch.from_numpy(alpha), blk(A0), n, c0) < 1e-13
+    Hbad = H.copy(); Hbad[3, 40] += 0.5
+    assert bench.column_norm_defect(torch, torch.from_numpy(np.ascontiguousarray(Hbad[:, 24:])), torch.from_numpy(alpha),
+                                    torch.from_numpy(np.ascontiguousarray(A0[:, 24:])), n, 24) > 1e-3
