@@ -224,10 +224,12 @@ def run_ours(args):
         try:
             A0 = D.colmajor_empty(m, nl, dev)
             D.fill_uniform_(A0, 0, 0, c0, h)
-            colnorm = maxover(column_norm_defect(torch, pool[(K - 1) % pool_n], alpha, A0, n, c0))
+            local_defect = column_norm_defect(torch, pool[(K - 1) % pool_n], alpha, A0, n, c0)
             del A0
-        except Exception as e:   # a failing check must not take the timing line with it
-            colnorm = f"check failed: {type(e).__name__}: {e}"
+        except Exception as e:   # a failing check must not take the timing line (or the other ranks) with it
+            sys.stderr.write(f"[bench] column-norm check failed on rank {rank}: {type(e).__name__}: {e}\n")
+            local_defect = float("inf")
+        colnorm = maxover(local_defect)   # the collective is outside the try: every rank reaches it
 
     # ---- per-kernel-class profile (separate, untimed step) -> roofline of the dominant kernel ----
     h.set_option("profile", 1)
