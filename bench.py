@@ -230,6 +230,8 @@ def run_ours(args):
             sys.stderr.write(f"[bench] column-norm check failed on rank {rank}: {type(e).__name__}: {e}\n")
             local_defect = float("inf")
         colnorm = maxover(local_defect)   # the collective is outside the try: every rank reaches it
+        if colnorm != colnorm or colnorm in (float("inf"), float("-inf")):
+            colnorm = "check failed (see stderr)"   # keep the line strict JSON
 
     # ---- per-kernel-class profile (separate, untimed step) -> roofline of the dominant kernel ----
     h.set_option("profile", 1)
