@@ -104,8 +104,8 @@ struct dhqr_context {
     // options
     int nb = 128, panel_ctas = 0, sync = 0, panel_backoff = 0, vta_max_chunks = 0, panel_levels = 2;
     // workspace
-    // two V buffers (panel k and panel k+1 live at the same time under look-ahead) and two workspace
-    // sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
+    // three V buffers (panels k, k+1 and the one being broadcast live at the same time under look-ahead) and two
+    // workspace sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
     double* vpk2[3] = {nullptr, nullptr, nullptr}; size_t vpk_elems[3] = {0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]
     struct WSet {
         double* wpart = nullptr; size_t wpart_elems = 0;                // gemm_vta partials
@@ -126,12 +126,12 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
-    int cvy_warps = 8;
-    int tail_cols = 0;                                               // trailing width below which the chain is considered critical
+    int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
+    int tail_cols = 0;                                                  // trailing width below which the chain is considered critical
     int wide_panel_ctas = 64;                                           // panel CTAs while the bulk update is wide
     bool bulk_wide = true;                                              // set per step by the look-ahead driver
     int panel_ctas_hint = 0;                                            // set per panel by the look-ahead driver (0 = default)
-    int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
+    int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
@@ -498,7 +498,7 @@ static int mirror_panel_to_host(dhqr_context* c, cudaStream_t st, const Panel& p
     return 0;
 }
 
-// single stream, one panel after the other (multi-GPU path; also option lookahead = 0)
+// single stream, one panel after the other (options lookahead = 0, sync, profile; any number of ranks)
 static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
                              double* alpha, const std::vector<Panel>& panels) {
     const int64_t lend = col0 + nl;

@@ -17,8 +17,10 @@
  *     legacy default stream) and the call returns without synchronising, except the _host_
  *     entry points, which block until their result is in host memory.
  *   - no pointer to caller memory is retained after return; workspace lives in the handle.
- *   - a handle is not thread-safe and serialises its calls on its own workspace: one handle per host
- *     thread (the reference is not re-entrant either: Polyester @batch, S:203-206).
+ *   - a handle is not thread-safe and its calls share one workspace: one handle per host thread, and
+ *     consecutive calls on one handle must be on the same stream or ordered by the caller (events);
+ *     the library does not order calls that arrive on different streams (the reference is not
+ *     re-entrant either: Polyester @batch, S:203-206).
  *   - SPMD for multi-GPU: every rank (one process per GPU) makes the same call with its own
  *     column block (col0 = first global column, 0-based = the reference's LocalColumnBlock.dj, S:34).
  *   - storage format on return == the reference's (S:127-135): Householder vectors scaled to
