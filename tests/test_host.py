@@ -63,3 +63,13 @@ def test_bench_column_norm_property_on_oracle_output():
     Hbad = H.copy(); Hbad[3, 40] += 0.5
     assert bench.column_norm_defect(torch, torch.from_numpy(np.ascontiguousarray(Hbad[:, 24:])), torch.from_numpy(alpha),
                                     torch.from_numpy(np.ascontiguousarray(A0[:, 24:])), n, 24) > 1e-3
+
+
+def test_tools_and_entry_scripts_compile():
+    """Every helper script shipped in the repo at least parses (they only run on a GPU box)."""
+    import glob, os, py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py", "dhqr_b200.py")]
+    assert len(files) > 5
+    for f in files:
+        py_compile.compile(f, doraise=True)
