@@ -23,6 +23,10 @@ constexpr int PANEL_THREADS = 512;
 #define DHQR_PANEL_VARIANT 4   // bit 2: triangular solves of the panel fast path on the fp64 tensor pipe (0: row-by-row
 #endif                         // substitution on the vector pipe); A/B results in profiles/r01_panel_variants.txt
 constexpr int PANEL_VARIANT = DHQR_PANEL_VARIANT;
+// Fast-path guard on the first Cholesky factor: min / max of its diagonal.  Row-by-row substitution is backward stable for
+// any factor the other guards accept (1e-5); the blocked solves invert 8x8 diagonal blocks explicitly, which costs
+// ~5e-18 x spread in ||QR - A|| / ||A|| (tests/test_fastpath_model.py), so they only take panels with a spread below 250.
+constexpr double FAST_SPREAD_MIN = (PANEL_VARIANT & 4) ? 4e-3 : 1e-5;
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier, TMA bulk copy, fp64 tensor-core MMA
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
     // reference's storage: v_ij = W_ij^(j) / sqrt(U_jj) (i > j), v_jj = -S_j sqrt(U_jj), alpha_j = S_j Rt_jj,
     // R_ij = S_i Rt_ij.  Same reflectors as S:127-135 up to rounding (verified against the oracle), but it
     // squares the panel's condition number on the way: if a Cholesky pivot is not positive, the first factor's
-    // diagonal spans more than 1e5, or Q1'Q1 is further than 1/4 from I (i.e. the second pass could not restore
+    // diagonal spans more than 250 (1e5 with substitution solves), or Q1'Q1 is further than 1/4 from I (i.e. the second pass could not restore
     // orthogonality to O(eps)), the slab is reloaded and the column-by-column path below runs instead
     // (that also reproduces the reference's NaN behaviour for zero columns).  The decision is taken from
     // identical data on every CTA, so it is grid-uniform without another exchange.
@@ -922,7 +926,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         if (tid == 0 && !bad) {   // conditioning guard on the first factor
             double dmin = R1[0], dmax = R1[0];
             for (int j = 1; j < IB; ++j) { dmin = fmin(dmin, R1[j * IB + j]); dmax = fmax(dmax, R1[j * IB + j]); }
-            if (!(dmin > 1e-5 * dmax)) bad = 1;
+            if (!(dmin > FAST_SPREAD_MIN * dmax)) bad = 1;
         }
         __syncthreads();
         if (!bad) {
