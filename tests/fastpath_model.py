@@ -108,3 +108,61 @@ def fast_panel(P):
                 H[i, j] = Sg[i] * Rt[i, j]
     alpha = Sg * np.diag(Rt)
     return H, alpha, True
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Design study for the next round (not what the kernel runs today): the two 32-step recurrences of the fast path in blocked
+# form, 8-column blocks, so that only 8x8 diagonal blocks stay serial and everything else is a small GEMM (tensor pipe).
+# ------------------------------------------------------------------------------------------------------------------------
+def cholesky_upper_blocked(G, bs=8):
+    """Upper Cholesky by bs-column blocks: serial factorisation of the diagonal block, row panel by a triangular solve with
+    the explicitly inverted diagonal block, trailing update by a rank-bs product.  Returns (R, rinv, ok)."""
+    g = np.array(G, dtype=np.float64, copy=True)
+    n = g.shape[0]
+    R = np.zeros((n, n))
+    rinv = np.zeros(n)
+    ok = True
+    for k in range(0, n, bs):
+        e = k + bs
+        d = g[k:e, k:e].copy()
+        Rd = np.zeros((bs, bs))
+        for j in range(bs):                                     # serial part: bs steps on a bs x bs block
+            p = d[j, j]
+            if not (p > 0.0) or not (p < 1e300):
+                ok = False
+                p = abs(p) + 1.0
+            ri = 1.0 / np.sqrt(p)
+            rinv[k + j] = ri
+            Rd[j, j:] = d[j, j:] * ri
+            Rd[j, j] = p * ri
+            for i in range(j + 1, bs):
+                d[i, i:] -= Rd[j, i] * Rd[j, i:]
+        R[k:e, k:e] = Rd
+        if e < n:
+            Rdinv = np.linalg.inv(Rd)                           # 8x8 triangular inverse (one thread per column in a kernel)
+            R[k:e, e:] = Rdinv.T @ g[k:e, e:]                   # R12 = Rd^{-T} G12
+            g[e:, e:] -= R[k:e, e:].T @ R[k:e, e:]              # G22 -= R12' R12
+    return R, rinv, ok
+
+
+def lu_signed_blocked(W, bs=8):
+    """The top-block LU of Householder reconstruction (signs S_j = -sign(pivot) picked on the fly, pivots U_jj = 1 + |w_jj|,
+    multipliers scaled by S_j / U_jj) in blocked right-looking form.  Returns (Wt, Sg, Ud) with the same meaning as the
+    unblocked loop in fast_panel: strict upper part = frozen rows U, strict lower part = W_ij^(j)."""
+    Wt = np.array(W, dtype=np.float64, copy=True)
+    n = Wt.shape[0]
+    Sg = np.zeros(n)
+    Ud = np.zeros(n)
+    for k in range(0, n, bs):
+        e = k + bs
+        for j in range(k, e):                                   # serial part, restricted to the block column / block row
+            w = Wt[j, j]
+            Sg[j] = -1.0 if w > 0.0 else 1.0
+            Ud[j] = 1.0 + abs(w)
+            f = Sg[j] / Ud[j]
+            Wt[j + 1:, j + 1:e] += np.outer(f * Wt[j + 1:, j], Wt[j, j + 1:e])      # columns inside the block: all rows below
+            Wt[j + 1:e, e:] += np.outer(f * Wt[j + 1:e, j], Wt[j, e:])              # rows inside the block: columns right of it
+        if e < n:                                               # trailing update with the block's multipliers: one GEMM
+            L = Wt[e:, k:e] * (Sg[k:e] / Ud[k:e])[None, :]      # -l_ij = f_j W_ij^(j)
+            Wt[e:, e:] += L @ Wt[k:e, e:]
+    return Wt, Sg, Ud

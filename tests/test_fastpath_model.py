@@ -76,3 +76,23 @@ def test_blocked_trsm_matches_substitution():
     X = rng.standard_normal((100, 32))
     Y = F.blocked_trsm(X, R, 1.0 / np.diag(R))
     assert np.abs(Y @ R - X).max() < 1e-12
+
+
+def test_design_study_blocked_recurrences_match_the_unblocked_ones(oracle):
+    # next-round design study: 8-column blocked Cholesky and signed LU give the factors of the 32-step recurrences
+    P = oracle.np_uniform(41, 1500, 32) - 0.3
+    G = P.T @ P
+    R, rinv, ok = F.cholesky_upper(G)
+    Rb, rinvb, okb = F.cholesky_upper_blocked(G)
+    assert ok and okb and np.abs(R - Rb).max() < 1e-12 * np.abs(R).max() and np.abs(rinv - rinvb).max() < 1e-12 * rinv.max()
+    Q = np.linalg.qr(P)[0][:32, :]
+    Wt = Q.copy()
+    Sg, Ud = np.zeros(32), np.zeros(32)
+    for j in range(32):
+        w = Wt[j, j]
+        Sg[j] = -1.0 if w > 0.0 else 1.0
+        Ud[j] = 1.0 + abs(w)
+        Wt[j + 1:, j + 1:] += np.outer(Sg[j] / Ud[j] * Wt[j + 1:, j], Wt[j, j + 1:])
+    Wb, Sgb, Udb = F.lu_signed_blocked(Q)
+    off = ~np.eye(32, dtype=bool)
+    assert np.array_equal(Sg, Sgb) and np.abs(Ud - Udb).max() < 1e-13 and np.abs((Wt - Wb)[off]).max() < 1e-13
