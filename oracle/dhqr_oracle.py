@@ -230,6 +230,72 @@ def np_ldiv(h, alpha, b):
     return np_backsolve(h, alpha, np_apply_qt(h, b))
 
 
+# ---------------------------------------------------------------------------
+# ComplexF64 restatement (SURVEY section 8f "next": oracle first; no CUDA path yet)
+# ---------------------------------------------------------------------------
+def np_alphafactor_c(x: complex) -> complex:
+    """S:9: alphafactor(x::Complex) = -exp(im * angle(x))   (angle(0) = 0 -> -1)."""
+    return -np.exp(1j * np.angle(x))
+
+
+def np_partialdot_c(a, b, i0, i1) -> complex:
+    """S:51-59: sum conj(a[i]) * b[i]   (re = ar*br + ai*bi, im = ar*bi - ai*br)."""
+    return complex(np.vdot(a[i0:i1], b[i0:i1]))
+
+
+def np_qr_c(a: np.ndarray):
+    """S:122-148 + S:198-213 for ComplexF64: H_j = I - v_j v_j^H with |v_j|^2 = 2, alpha_j = -exp(i angle(h_jj)) * norm."""
+    h = np.array(a, dtype=np.complex128, order="F", copy=True)
+    m, n = h.shape
+    alpha = np.zeros(n, dtype=np.complex128)
+    for j in range(n):
+        s = np.linalg.norm(h[j:, j])                      # S:129
+        alpha[j] = s * np_alphafactor_c(h[j, j])          # S:130
+        f = 1.0 / np.sqrt(s * (s + abs(h[j, j])))         # S:131 (real)
+        h[j, j] -= alpha[j]                               # S:132
+        h[j:, j] *= f                                     # S:133-135
+        hj = h[:, j].copy()                               # S:138-140
+        if j + 1 < n:
+            s_all = np.conj(hj[j:]) @ h[j:, j + 1:]       # S:208 with the complex partialdot (S:51-59)
+            h[j:, j + 1:] -= np.outer(hj[j:], s_all)      # S:209 / S:162-196 (hotloop!: Hl -= Hj * s)
+    return h, alpha
+
+
+def np_apply_qt_c(h, b):
+    """S:232-242 with the complex partialdot."""
+    m, n = h.shape
+    w = np.array(b, dtype=np.complex128, copy=True)
+    for j in range(n):
+        s = np.vdot(h[j:, j], w[j:])
+        w[j:] -= h[j:, j] * s
+    return w
+
+
+def np_backsolve_c(h, alpha, b):
+    """S:244-254 (no conjugation: plain triangular solve with diag(R) = alpha)."""
+    m, n = h.shape
+    w = np.array(b, dtype=np.complex128, copy=True)
+    for i in range(n - 1, -1, -1):
+        w[i] = (w[i] - h[i, i + 1:n] @ w[i + 1:n]) / alpha[i]
+    return w[:n]
+
+
+def np_ldiv_c(h, alpha, b):
+    """S:317-321."""
+    return np_backsolve_c(h, alpha, np_apply_qt_c(h, b))
+
+
+def reconstruct_c(h, alpha):
+    """Q R from the complex storage format: R = triu(H,1) + diag(alpha), Q = H_1 ... H_n."""
+    m, n = h.shape
+    r = np.zeros((m, n), dtype=np.complex128)
+    r[:n] = np.triu(h[:n], 1) + np.diag(alpha)
+    for j in range(n - 1, -1, -1):
+        v = h[j:, j]
+        r[j:] -= np.outer(v, np.conj(v) @ r[j:])
+    return r
+
+
 def np_uniform(seed: int, m: int, n: int, i0: int = 0, j0: int = 0) -> np.ndarray:
     """numpy twin of dhqr_oracle_fill_uniform (counter-based U[0,1) keyed on (seed, i, j))."""
     def mix(z):

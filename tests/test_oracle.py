@@ -127,3 +127,50 @@ def test_qr_steps_prefix(coracle):
     full = A.copy(order="F"); _, afull = coracle.qr(full)
     part = A.copy(order="F"); apart, fl = coracle.qr_steps(part, 10)
     assert np.array_equal(apart[:10], afull[:10]) and np.array_equal(part[:, :10], full[:, :10]) and fl > 0
+
+
+# ---- ComplexF64 restatement (SURVEY 8f "next": oracle first) ----------------------------------------------------------
+def _complex_matrix(oracle, seed, m, n):
+    return (oracle.np_uniform(seed, m, n) - 0.5) + 1j * (oracle.np_uniform(seed + 100, m, n) - 0.5)
+
+
+@pytest.mark.parametrize("m,n", [(110, 100), (300, 37), (64, 64)])
+def test_complex_restatement_reconstructs_and_solves(oracle, m, n):
+    A = _complex_matrix(oracle, 5, m, n)
+    H, alpha = oracle.np_qr_c(A)
+    # reflectors are scaled to |v|^2 = 2 (H_j = I - v v^H is unitary) and |alpha_j| is the column norm at step j
+    for j in range(n):
+        assert abs(np.vdot(H[j:, j], H[j:, j]).real - 2.0) < 1e-12
+    assert np.linalg.norm(oracle.reconstruct_c(H, alpha) - A) / np.linalg.norm(A) < 1e-13
+    # the reference's test property (T:51/62/81): normal-equation residual within 8x of LAPACK's least-squares solve
+    b = _complex_matrix(oracle, 9, m, 1)[:, 0]
+    x = oracle.np_ldiv_c(H, alpha, b)
+    xl = np.linalg.lstsq(A, b, rcond=None)[0]
+    ne = lambda z: np.linalg.norm(A.conj().T @ (A @ z - b))
+    assert ne(x) < 8 * max(ne(xl), 1e-13 * np.linalg.norm(A) ** 2 * np.linalg.norm(xl))
+    assert np.abs(x - xl).max() < 1e-9 * np.abs(xl).max()
+
+
+def test_complex_restatement_against_lapack_zgeqrf(oracle):
+    # QR is unique up to a unitary diagonal: row j of the reference's R is LAPACK's row j times the phase alpha_j / beta_j,
+    # and |alpha_j| = |R_lapack[j, j]|
+    from scipy.linalg import lapack
+    A = _complex_matrix(oracle, 11, 200, 48)
+    H, alpha = oracle.np_qr_c(A)
+    qr, tau, _, info = lapack.zgeqrf(np.asfortranarray(A))
+    assert info == 0
+    Rl = np.triu(qr[:48])
+    Rr = np.triu(H[:48], 1) + np.diag(alpha)
+    phase = alpha / np.diag(Rl)
+    assert np.abs(np.abs(phase) - 1.0).max() < 1e-12
+    assert np.abs(Rr - phase[:, None] * Rl).max() < 1e-11 * np.abs(Rl).max()
+
+
+def test_complex_alphafactor_and_partialdot(oracle):
+    assert oracle.np_alphafactor_c(0.0) == -1.0                                  # angle(0) = 0 (S:9), unlike sign(0) = 0 (S:8)
+    z = 3.0 - 4.0j
+    assert abs(oracle.np_alphafactor_c(z) + z / abs(z)) < 1e-15
+    a = _complex_matrix(oracle, 1, 50, 1)[:, 0]
+    b = _complex_matrix(oracle, 2, 50, 1)[:, 0]
+    for i0 in (0, 7, 49):                                                        # every suffix, test/partialdot.jl:11-22
+        assert abs(oracle.np_partialdot_c(a, b, i0, 50) - np.sum(np.conj(a[i0:]) * b[i0:])) < 1e-13
