@@ -3,12 +3,14 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module; the product path (libdhqr.so + the dhqr_b200 host package) never does.
 
-Three things live here, each citing the reference lines it follows
+Four things live here, each citing the reference lines it follows
 (S:n = /root/reference/src/DistributedHouseholderQR.jl:n, T:n = test/runtests.jl:n):
 
 * ``COracle``  — ctypes binding of oracle/dhqr_oracle.c (the C restatement, OpenMP threads over
   trailing-column chunks like S:203-211).
 * ``np_*``     — a pure-numpy twin of the same recurrences (small cases; independent code path).
+* ``np_*_c``   — the same recurrences for ComplexF64 (S:9, S:51-59, S:162-196; the reference tests both element types,
+  T:43): oracle only so far, there is no complex CUDA path to check against it yet.
 * ``lapack_*`` — LAPACK dgeqrf mapped into the reference's storage format (alpha = diag R,
   triu(H,1) = triu(R,1), v_ref = -sign(alpha) * sqrt(tau) * [1; v_lapack]): the "stdlib" comparator
   the reference's own tests normalise to (T:49-51).
