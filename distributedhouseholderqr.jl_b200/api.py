@@ -183,6 +183,30 @@ def splits(nranks: int, n: int):
     return b
 
 
+def balanced_splits(nranks: int, n: int, rule: str = "trailing"):
+    """Load-balanced contiguous column splits; the reference carries two of them next to its DArray test (unused there:
+    the code that would consume them, T:67-68, is commented out).
+
+    rule="trailing": splits(np, N, p) = round((N / sqrt(np)) * sqrt(p))  (T:35) — column c is updated by the c reflectors
+                     to its left, so equal work means equal areas under that ramp: early ranks get MORE columns.  This is
+                     the split that evens out the trailing-update flops of the right-looking factorisation.
+    rule="upstream": splits(np, N, p) = round(N * (1 - sqrt((np - p) / np)))  (T:36, the definition left active upstream) —
+                     the mirror image (early ranks get fewer columns).
+
+    Any contiguous, ascending partition is accepted by the C-ABI; pass the result as ``boundaries`` to
+    ColumnBlockMatrix.from_function."""
+    if rule == "trailing":
+        b = [int(round(n * (p / nranks) ** 0.5)) for p in range(nranks + 1)]
+    elif rule == "upstream":
+        b = [int(round(n * (1.0 - ((nranks - p) / nranks) ** 0.5))) for p in range(nranks + 1)]
+    else:
+        raise ValueError("rule must be 'trailing' or 'upstream'")
+    b[0], b[-1] = 0, n
+    for p in range(1, nranks + 1):          # monotone even for tiny n
+        b[p] = max(b[p], b[p - 1])
+    return b
+
+
 @dataclass
 class LocalColumnBlock:
     """LocalColumnBlock{Al, dj, colrange} (S:26-40): local storage + global column offset."""
@@ -211,10 +235,13 @@ class ColumnBlockMatrix:
         return LocalColumnBlock(self.local, self.col0, range(self.col0, self.col0 + self.local.shape[1]))
 
     @classmethod
-    def from_function(cls, fill, m: int, n: int, handle: Handle):
+    def from_function(cls, fill, m: int, n: int, handle: Handle, boundaries=None):
         """DArray(ij -> A[ij...], (m,n), workers(), (1, nworkers())) (T:71): ``fill(col0, ncols)``
-        returns the (m, ncols) block for this rank."""
-        b = splits(handle.nranks, n)
+        returns the (m, ncols) block for this rank.  ``boundaries`` (P+1 ascending column boundaries, same on every rank)
+        overrides the default distribution, e.g. ``balanced_splits(P, n)`` (T:35-36)."""
+        b = list(boundaries) if boundaries is not None else splits(handle.nranks, n)
+        if len(b) != handle.nranks + 1 or b[0] != 0 or b[-1] != n or any(b[i] > b[i + 1] for i in range(handle.nranks)):
+            raise ValueError(f"boundaries must be {handle.nranks + 1} ascending values from 0 to n={n}, got {b}")
         c0, c1 = b[handle.rank], b[handle.rank + 1]
         return cls(to_colmajor(fill(c0, c1 - c0), device=f"cuda:{handle.device}"), n, c0, handle)
 

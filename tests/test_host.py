@@ -73,3 +73,27 @@ def test_tools_and_entry_scripts_compile():
     assert len(files) > 5
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_balanced_splits_follow_the_reference_formulas():
+    # T:35: round((N / sqrt(np)) * sqrt(p))   and   T:36: round(N * (1 - sqrt((np - p) / np)))
+    for P, n in ((2, 4096), (4, 4096), (8, 8192), (3, 100), (4, 3)):
+        for rule, f in (("trailing", lambda p: n * (p / P) ** 0.5), ("upstream", lambda p: n * (1 - ((P - p) / P) ** 0.5))):
+            b = D.balanced_splits(P, n, rule)
+            assert len(b) == P + 1 and b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(P))
+            for p in range(1, P):
+                assert b[p] == max(b[p - 1], int(round(f(p))))
+    assert D.balanced_splits(2, 4096, "upstream") == [0, 1200, 4096]
+    assert D.balanced_splits(2, 4096) == [0, 2896, 4096]
+    with pytest.raises(ValueError):
+        D.balanced_splits(2, 10, "nope")
+    # trailing-update work of the right-looking factorisation per rank: reflector j (length m - j) touches the local columns
+    # right of j.  The T:35 split evens it out compared with the default distribution; the T:36 split does the opposite.
+    m, n, P = 32768, 4096, 4
+
+    def work(bounds):
+        j = np.arange(n)
+        return np.array([float(np.sum((m - j) * np.clip(bounds[p + 1] - np.maximum(j + 1, bounds[p]), 0, None))) for p in range(P)])
+
+    imb = lambda w: w.max() / w.mean()
+    assert imb(work(D.balanced_splits(P, n))) < 1.1 < imb(work(D.splits(P, n))) < imb(work(D.balanced_splits(P, n, "upstream")))
