@@ -60,3 +60,26 @@ def test_argument_errors_are_lapack_style():
     assert lib.dhqr_set_option(None, b"nb", 64) == -1
     assert b"null handle" in lib.dhqr_last_error()
     assert lib.dhqr_create(None, 0) == -1
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/dhqr.h must be consumable by a C compiler (cgo / ccall / ctypes users never see C++), and every declared
+    function must resolve against libdhqr.so at link time."""
+    import re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "dhqr.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|const char \*)\s*(dhqr_[a-z0-9_]+)\s*\(", hdr, flags=re.M)))
+    assert len(names) >= 20
+    src = tmp_path / "use.c"
+    body = "\n".join(f"    p[{i}] = (fn_t)&{n};" for i, n in enumerate(names))
+    src.write_text('#include "dhqr.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n    fn_t p[%d];\n%s\n'
+                   '    printf("%%d %%d\\n", dhqr_version(), (int)(sizeof(p) / sizeof(p[0])));\n    return p[0] == 0;\n}\n' % (len(names), body))
+    exe = tmp_path / "use"
+    libdir = os.path.join(root, "distributedhouseholderqr.jl_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libdhqr.so", f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    if out.returncode == 0:                      # loads without a GPU as long as libcudart resolves; no CUDA call is made
+        ver, cnt = out.stdout.split()
+        assert int(ver) == 100 and int(cnt) == len(names)
