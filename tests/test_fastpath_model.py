@@ -96,3 +96,23 @@ def test_design_study_blocked_recurrences_match_the_unblocked_ones(oracle):
     Wb, Sgb, Udb = F.lu_signed_blocked(Q)
     off = ~np.eye(32, dtype=bool)
     assert np.array_equal(Sg, Sgb) and np.abs(Ud - Udb).max() < 1e-13 and np.abs((Wt - Wb)[off]).max() < 1e-13
+
+
+def test_kahan_like_panels_high_condition_without_a_small_pivot(oracle):
+    # Kahan-type factors are ill-conditioned with a slowly decaying diagonal, so the spread guard alone does not see them;
+    # accepted panels must still be backward stable and the orthogonality guard must refuse them before CholeskyQR2 breaks
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.standard_normal((2048, 32)))
+    accepted = refused = 0
+    for theta in (1.5, 1.4, 1.3, 1.2, 1.1, 1.0, 0.9):
+        c, s = np.cos(theta), np.sin(theta)
+        R = np.diag(s ** np.arange(32)) @ (np.eye(32) - c * np.triu(np.ones((32, 32)), 1))
+        P = Q @ R
+        H, alpha, fast = F.fast_panel(P)
+        if fast:
+            accepted += 1
+            assert oracle.qr_residual(P, np.asfortranarray(H), alpha) < 3e-15
+        else:
+            refused += 1
+            assert np.linalg.cond(P) > 1e7
+    assert accepted >= 4 and refused >= 1
