@@ -35,6 +35,7 @@ SIGNATURES = {
     "dhqr_k_block_reflector_f64": [_vp, _i64, _int, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp],
     "dhqr_debug_copy_f64": [_vp, C.c_char_p, _vp, _i64, _vp],
     "dhqr_k_panel_f64": [_vp, _i64, _int, _vp, _i64, _vp, _vp],
+    "dhqr_k_wide_panel_f64": [_vp, _i64, _vp, _i64, _vp, C.POINTER(_int), _vp],
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "dhqr_kernels.cuh"
+#include "dhqr_wide.cuh"
 
 using namespace dhqr;
 
@@ -133,6 +134,11 @@ struct dhqr_context {
     int panel_ctas_hint = 0;                                            // set per panel by the look-ahead driver (0 = default)
     int hp_max_ctas = 0;                                                // cap on gemm_vta CTAs of the panel chain under look-ahead (0 = none)
     long long* panel_trace = nullptr;                                   // optional k_panel clock stamps (option "panel_trace")
+    // 128-column panel chain (dhqr_wide.cuh)
+    int wide_panel = 1;                                                 // option: factor full aligned outer panels with CholeskyQR2 + reconstruction
+    WideCtl* wctl = nullptr;                                            // device control words (first refused panel, guards of the panel in flight)
+    double* wbuf = nullptr;                                             // R1, R2, X2, Rt, Y3 (plain 128x128) + XL, XL3 (rmul operand layout)
+    int64_t wide_panels = 0, wide_redone = 0;                           // statistics: panels factored by the wide chain / factorisations restarted
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
     double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
@@ -188,6 +194,9 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
     CU(cudaFuncSetAttribute(k_ymake<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(32)));
     CU(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 184 * 1024));
+    CU(cudaFuncSetAttribute(k_chol128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_WIDE1));
+    CU(cudaFuncSetAttribute(k_hr128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_WIDE1));
+    CU(cudaFuncSetAttribute(k_vpk_rmul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_RMUL));
     CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->attrs_set = true;
     return 0;
@@ -235,6 +244,13 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         c->ll_epoch = 0;
     }
     if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)IB * (PANEL_MAXG + 2) * IB * 2)); c->ll_epoch = 0; }
+    if (!c->wctl) {
+        CU(cudaMalloc((void**)&c->wctl, sizeof(WideCtl)));
+        const WideCtl init = {W_NOFAIL, 0};
+        CU(cudaMemcpy(c->wctl, &init, sizeof(init), cudaMemcpyHostToDevice));
+        size_t o3 = 0;
+        TRY(ensure(&c->wbuf, &o3, (size_t)5 * WP * WP + 2 * XL_ELEMS));
+    }
     TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
     return 0;
@@ -305,7 +321,7 @@ static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t 
 //   Gram matrix; `w` = the workspace set of the calling chain.
 static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int voff, int nbp,
                                  int64_t rows, int64_t row_lo, double* C, int64_t ldc, int ncols, int max_chunks = 0,
-                                 bool reuse_T = false, double* linv_io = nullptr) {
+                                 bool reuse_T = false, double* linv_io = nullptr, int gate = 0) {
     double* linv = linv_io ? linv_io : w.linv;   // where T' is written (or read from, with reuse_T)
     // reuse_T: w.linv already holds T' of this V (same chain, previous call) -> skip the Gram block and k_tinv
     if (ncols <= 0 || rows <= 0) return 0;
@@ -361,6 +377,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g2.vpk = vpk; g2.voff = voff; g2.ypk = w.ypk;
     g2.nkq = small ? 1 : (int)(rup(nbp, KC) / KC); g2.nkq_alloc = NBPK / KC;
     g2.sm_ticket = c->cvy_stagger ? c->sm_ticket : nullptr; g2.first_wave = 2 * c->sms; g2.stagger_cycles = 5200 * g2.nkq;
+    g2.ctl = c->wctl; g2.gate = gate;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
     if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
@@ -372,7 +389,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
 // cooperative panel launch: factor mp x ncols (<= IB) at P, V block -> vout columns
 // ------------------------------------------------------------------------------------------------
 static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P, int64_t ldp, int64_t mp, int ncols,
-                        double* alpha, int voff, int64_t vtop, int64_t vrows) {
+                        double* alpha, int voff, int64_t vtop, int64_t vrows, int gate = 0) {
     int gmax = c->panel_ctas > 0 ? c->panel_ctas : (c->panel_ctas_hint > 0 ? c->panel_ctas_hint : (c->lookahead ? 64 : c->sms));
     gmax = std::min(std::min(gmax, c->sms), PANEL_MAXG);
     int64_t rpc = std::max<int64_t>((mp + gmax - 1) / gmax, 64);
@@ -396,6 +413,7 @@ static int launch_panel(dhqr_context* c, cudaStream_t st, double* vpk, double* P
     a.rows_per_cta = (int)rpc; a.lds = lds;
     a.cells = c->cells; a.epoch = c->ll_epoch; a.trace = c->panel_trace; a.backoff = c->panel_backoff; a.levels = c->panel_levels;
     a.cells2 = c->cells2; a.fast = c->panel_fast; a.fast_stats = c->fast_stats;
+    a.ctl = c->wctl; a.gate = gate;
     void* args[] = {&a};
     pre(c, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(PANEL_THREADS), args, smem, st);
@@ -466,23 +484,101 @@ static PanelGeom panel_geom(const Panel& p, int64_t m) {
 }
 
 // factor one outer panel on stream st: inner panels of IB columns + updates inside the outer panel; V -> vpk
-static int factor_outer_panel(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
-                              int64_t col0, double* A, int64_t lda, double* alpha) {
+// (the 32-column chain: one cooperative launch per inner panel, S:127-135 column by column in the worst case)
+static int factor_outer_panel_narrow(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
+                                     int64_t col0, double* A, int64_t lda, double* alpha, int step) {
     const PanelGeom g = panel_geom(p, m);
     for (int o = 0; o < p.kb; o += IB) {
         const int ib = std::min(IB, p.kb - o);
         const int64_t cs = p.c + o;                                   // global column == pivot row
         double* P = A + (cs - col0) * lda + cs;
-        TRY(launch_panel(c, st, vpk, P, lda, m - cs, ib, alpha + cs, o, cs - g.r0, g.vrows));
+        TRY(launch_panel(c, st, vpk, P, lda, m - cs, ib, alpha + cs, o, cs - g.r0, g.vrows, step));
         const int rem = p.kb - (o + ib);
         if (rem > 0)   // update the rest of the outer panel with this sub-panel's reflectors
-            TRY(apply_block_reflector(c, st, vpk, w, o, IB, g.rows, cs - g.r0, A + (cs + ib - col0) * lda + g.r0, lda, rem));
+            TRY(apply_block_reflector(c, st, vpk, w, o, IB, g.rows, cs - g.r0, A + (cs + ib - col0) * lda + g.r0, lda, rem, 0, false,
+                                      nullptr, step));
     }
     if (g.nbp > IB && g.nbp < NBMAX) {   // zero the V columns the 128-wide kernels read beyond nbp
         k_vpk_zero_cols<<<2 * c->sms, 256, 0, st>>>(vpk, g.vrows / KC1, g.nbp, NBMAX);
         TRY(post(c, st, "k_vpk_zero_cols"));
     }
     return 0;
+}
+
+// Gram matrix of the packed panel: wsum(128 x 128) = vpk' vpk over `rows` window rows (k_gemm_vta with no trailing columns)
+static int wide_gram(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int64_t rows) {
+    const int tiles = WP / G1_BN;
+    const int nchunks = (int)((rows + KC1 - 1) / KC1);
+    const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
+    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
+    GemmVtaArgs g1;
+    g1.vpk = vpk; g1.voff = 0; g1.nv = WP; g1.A = vpk; g1.lda = 2; g1.rows = rows; g1.na = 0; g1.nchunks = nchunks;
+    g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
+    pre(c, st);
+    K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
+    TRY(post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP));
+    pre(c, st);
+    k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
+    return post(c, st, "k_wreduce");
+}
+
+// the 128-column chain (dhqr_wide.cuh): CholeskyQR2 + Householder reconstruction of a full aligned outer panel
+static bool wide_eligible(const dhqr_context* c, const Panel& p, int64_t m, int nb) {
+    return c->wide_panel && nb == WP && p.kb == WP && (p.c & 31) == 0 && m - p.c >= WP;
+}
+static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
+                                   int64_t col0, double* A, int64_t lda, double* alpha, int step) {
+    const PanelGeom g = panel_geom(p, m);       // r0 == p.c: the window starts at the pivot row
+    double* P = A + (p.c - col0) * lda + p.c;
+    double* R1 = c->wbuf, *R2 = R1 + WP * WP, *X2 = R2 + WP * WP, *Rt = X2 + WP * WP, *Y3 = Rt + WP * WP;
+    double* XL = Y3 + WP * WP, *XL3 = XL + XL_ELEMS;
+    double* vflag = vpk + KC1;                  // padding row 64 of packed column 0: travels with the V buffer
+    const int nq = (int)(g.vrows / KC1);
+    RmulArgs r;
+    r.vpk = vpk; r.ctl = c->wctl; r.step = step; r.P = nullptr; r.ldp = lda; r.mp = g.rows;
+    auto rmul = [&](int q0, int n, const double* X, double* Pout) -> int {
+        if (n <= 0) return 0;
+        r.q0 = q0; r.nq = n; r.XL = X; r.P = Pout;
+        pre(c, st);
+        k_vpk_rmul<<<std::min(n, c->sms), 256, SMEM_RMUL, st>>>(r);
+        return post(c, st, "k_vpk_rmul", 2.0 * 64.0 * n * WP * 80.0);
+    };
+    pre(c, st);
+    dim3 pgrid((unsigned)std::min<int64_t>((g.vrows + 255) / 256, 4 * c->sms), WP);
+    k_pack<<<pgrid, 256, 0, st>>>(P, lda, g.rows, WP, 0, vpk, 0, 0, g.vrows);
+    TRY(post(c, st, "k_pack"));
+    TRY(wide_gram(c, st, vpk, w, g.rows));
+    pre(c, st);
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, nullptr, XL, c->wctl, step, vflag);
+    TRY(post(c, st, "k_chol128"));
+    TRY(rmul(0, nq, XL, nullptr));
+    TRY(wide_gram(c, st, vpk, w, g.rows));
+    pre(c, st);
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, X2, XL, c->wctl, step, vflag);
+    TRY(post(c, st, "k_chol128"));
+    pre(c, st);
+    k_trimm128<<<10, 256, 0, st>>>(R2, R1, Rt, nullptr, c->wctl, step);
+    TRY(post(c, st, "k_trimm128"));
+    TRY(rmul(0, 2, XL, nullptr));
+    pre(c, st);
+    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Y3, c->wctl, step);
+    TRY(post(c, st, "k_hr128"));
+    pre(c, st);
+    k_trimm128<<<10, 256, 0, st>>>(X2, Y3, nullptr, XL3, c->wctl, step);
+    TRY(post(c, st, "k_trimm128"));
+    TRY(rmul(2, nq - 2, XL3, P));
+    c->wide_panels++;
+    return 0;
+}
+
+static int factor_outer_panel(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
+                              int64_t col0, double* A, int64_t lda, double* alpha, int step, bool wide) {
+    if (c->wctl) {   // clear the guards of the previous panel and the verdict that travels with this V buffer
+        k_wide_begin<<<1, 32, 0, st>>>(c->wctl, vpk + KC1);
+        TRY(post(c, st, "k_wide_begin"));
+    }
+    if (wide) return factor_outer_panel_wide(c, st, vpk, w, p, m, col0, A, lda, alpha, step);
+    return factor_outer_panel_narrow(c, st, vpk, w, p, m, col0, A, lda, alpha, step);
 }
 
 static int mirror_panel_to_host(dhqr_context* c, cudaStream_t st, const Panel& p, int64_t m, int64_t col0, const double* A,
@@ -498,35 +594,44 @@ static int mirror_panel_to_host(dhqr_context* c, cudaStream_t st, const Panel& p
     return 0;
 }
 
+// Which panels go through the 128-column chain: those at or beyond `wide_from` that are full and aligned.
+struct Plan { int kstart; int wide_from; int nb; };
+static bool plan_wide(const dhqr_context* c, const Plan& pl, const std::vector<Panel>& panels, int k, int64_t m) {
+    return k >= pl.wide_from && wide_eligible(c, panels[k], m, pl.nb);
+}
+
 // single stream, one panel after the other (options lookahead = 0, sync, profile; any number of ranks)
 static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
-                             double* alpha, const std::vector<Panel>& panels) {
+                             double* alpha, const std::vector<Panel>& panels, const Plan& pl) {
     const int64_t lend = col0 + nl;
     double* vpk = c->vpk2[0];
     auto& w = c->ws[0];
-    for (const Panel& p : panels) {
+    for (int k = pl.kstart; k < (int)panels.size(); ++k) {
+        const Panel& p = panels[k];
         const PanelGeom g = panel_geom(p, m);
         if (c->rank == p.owner) {
-            TRY(factor_outer_panel(c, st, vpk, w, p, m, col0, A, lda, alpha));
+            TRY(factor_outer_panel(c, st, vpk, w, p, m, col0, A, lda, alpha, k, plan_wide(c, pl, panels, k, m)));
             TRY(mirror_panel_to_host(c, st, p, m, col0, A, lda));
         }
         if (c->nranks > 1) {
             // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
             NC(g_nccl.Broadcast(vpk, vpk, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, p.owner, c->comm, st));
             NC(g_nccl.Broadcast(alpha + p.c, alpha + p.c, (size_t)p.kb, ncclFloat64, p.owner, c->comm, st));
+            k_wide_note<<<1, 32, 0, st>>>(c->wctl, vpk + KC1, k);
+            TRY(post(c, st, "k_wide_note"));
         }
         // trailing update of the local columns right of the panel (S:198-213 for nb columns at once)
         const int64_t t0 = std::max(p.c + p.kb, col0);
         if (t0 < lend)
-            TRY(apply_block_reflector(c, st, vpk, w, 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda, (int)(lend - t0)));
+            TRY(apply_block_reflector(c, st, vpk, w, 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda, (int)(lend - t0), 0,
+                                      false, nullptr, k + 1));
     }
     return 0;
 }
 
-// look-ahead: the panel chain (latency bound: one grid-wide exchange per column) runs on a high-priority
-// stream ahead of the bulk trailing update, which stays on the caller's stream.  SPMD over ranks: the owner
-// of a panel factors it, the packed V block is broadcast on the high-priority stream (the only stream that
-// issues collectives), every rank updates its own columns.
+// look-ahead: the panel chain (latency bound) runs on a high-priority stream ahead of the bulk trailing update, which stays on
+// the caller's stream.  SPMD over ranks: the owner of a panel factors it, the packed V block is broadcast on the high-priority
+// stream (the only stream that issues collectives), every rank updates its own columns.
 //   hp step k: wait next[k-1];  owner(k+1): apply V_k -> columns of panel k+1, factor panel k+1 (V -> vpk[(k+1)%3]);
 //              broadcast vpk[(k+1)%3] + alpha slice;  signal panel[k+1]                                    set 1
 //   st step k: wait panel[k];   (a) apply V_k -> local columns of panel k+2, signal next[k];
@@ -535,13 +640,13 @@ static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_
 // (a) parts, i.e. it has two bulk updates of slack.  Three V buffers: V_{k+2} replaces V_{k-1}, whose last
 // reader (b)_{k-1} precedes (a)_k on st (hence the wait on next[k-1] on every rank before the broadcast).
 static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, double* A, int64_t lda,
-                                double* alpha, const std::vector<Panel>& panels) {
+                                double* alpha, const std::vector<Panel>& panels, const Plan& pl) {
     const int64_t lend = col0 + nl;
-    const int K = (int)panels.size();
+    const int K = (int)panels.size(), K0 = pl.kstart;
     cudaStream_t hp = c->hp_stream;
     std::vector<cudaEvent_t> evPanel(K), evNext(K), evBulk(K);
     const unsigned evflags = c->la_trace ? cudaEventDefault : cudaEventDisableTiming;
-    for (int k = 0; k < K; ++k) {
+    for (int k = K0; k < K; ++k) {
         CU(cudaEventCreateWithFlags(&evPanel[k], evflags));
         CU(cudaEventCreateWithFlags(&evNext[k], evflags));
         CU(cudaEventCreateWithFlags(&evBulk[k], evflags));
@@ -556,22 +661,24 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             double* v = c->vpk2[k % 3];
             NC(g_nccl.Broadcast(v, v, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, panels[k].owner, c->comm, hp));
             NC(g_nccl.Broadcast(alpha + panels[k].c, alpha + panels[k].c, (size_t)panels[k].kb, ncclFloat64, panels[k].owner, c->comm, hp));
+            k_wide_note<<<1, 32, 0, hp>>>(c->wctl, v + KC1, k);   // the owner's verdict on the panel arrived with the buffer
+            TRY(post(c, hp, "k_wide_note"));
         }
         CU(cudaEventRecord(evPanel[k], hp));
         return 0;
     };
     int rc = 0;
-    cudaEvent_t fork = nullptr;
+    cudaEvent_t fork = nullptr, hpdone = nullptr;
     do {
         if (cudaEventCreateWithFlags(&fork, evflags) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
         cudaEventRecord(fork, st);
         cudaStreamWaitEvent(hp, fork, 0);                          // hp starts after everything already queued on st
-        if (c->rank == panels[0].owner) {
-            if ((rc = factor_outer_panel(c, hp, c->vpk2[0], c->ws[1], panels[0], m, col0, A, lda, alpha))) break;
-            if ((rc = mirror_panel_to_host(c, hp, panels[0], m, col0, A, lda))) break;
+        if (c->rank == panels[K0].owner) {
+            if ((rc = factor_outer_panel(c, hp, c->vpk2[K0 % 3], c->ws[1], panels[K0], m, col0, A, lda, alpha, K0, plan_wide(c, pl, panels, K0, m)))) break;
+            if ((rc = mirror_panel_to_host(c, hp, panels[K0], m, col0, A, lda))) break;
         }
-        if ((rc = publish(0))) break;
-        for (int k = 0; k < K && !rc; ++k) {
+        if ((rc = publish(K0))) break;
+        for (int k = K0; k < K && !rc; ++k) {
             const Panel& p = panels[k];
             const PanelGeom g = panel_geom(p, m);
             const double* vk = c->vpk2[k % 3];
@@ -584,18 +691,19 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             bool haveT = false;                                          // T'_k in lk (this rank)
             if (k + 1 < K) {
                 // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2
-                if (k > 1) cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
+                if (k - 2 >= K0) cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
                 if (c->rank == panels[k + 1].owner) {
                     if (clip(t0, t1, lo, hi)) {
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
-                                                        lda, (int)(hi - lo), 0, false, lk))) break;
+                                                        lda, (int)(hi - lo), 0, false, lk, k + 1))) break;
                         haveT = true;
                         cudaEventRecord(evNext[k], hp);                  // T'_k is in the ring: the bulk update may start
                     }
                     // while the bulk update is wide the panel kernel leaves most SMs to it (64 CTAs); once the trailing
                     // matrix is narrow the chain is the critical path and the panel takes every SM
                     c->panel_ctas_hint = c->bulk_wide ? c->wide_panel_ctas : (c->tail_cols > 0 ? c->sms : c->wide_panel_ctas);
-                    rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha);
+                    rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha, k + 1,
+                                            plan_wide(c, pl, panels, k + 1, m));
                     c->panel_ctas_hint = 0;
                     if (rc) break;
                     if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
@@ -604,10 +712,10 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             }
             // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1
             if (clip(t1, t2, lo, hi)) {
-                if (k > 0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
+                if (k - 1 >= K0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
                 const bool hadT = haveT;
                 if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
-                                                (int)(hi - lo), 0, haveT, lk))) break;
+                                                (int)(hi - lo), 0, haveT, lk, k + 1))) break;
                 haveT = true;
                 if (!hadT) cudaEventRecord(evNext[k], hp);               // T'_k came from this apply
             }
@@ -616,7 +724,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             if (clip(t2, lend, lo, hi)) {
                 if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);
                 if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
-                                                (int)(hi - lo), maxch, haveT, haveT ? lk : nullptr))) break;
+                                                (int)(hi - lo), maxch, haveT, haveT ? lk : nullptr, k + 1))) break;
             }
             cudaEventRecord(evBulk[k], st);
         }
@@ -627,21 +735,34 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             cudaStreamSynchronize(st);
             cudaStreamSynchronize(hp);
             c->la_times.assign((size_t)K * 3, 0.f);
-            for (int k = 0; k < K; ++k) {
+            for (int k = K0; k < K; ++k) {
                 cudaEventElapsedTime(&c->la_times[3 * k + 0], fork, evPanel[k]);
                 cudaEventElapsedTime(&c->la_times[3 * k + 1], fork, evNext[k]);
                 cudaEventElapsedTime(&c->la_times[3 * k + 2], fork, evBulk[k]);
             }
         }
     } while (0);
+    // error path: the caller's stream must not run ahead of (or return before) work already queued on the internal stream
+    if (rc && cudaEventCreateWithFlags(&hpdone, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(hpdone, hp);
+        cudaStreamWaitEvent(st, hpdone, 0);
+        cudaEventDestroy(hpdone);
+    }
     // events may be destroyed once recorded/waited on: the work they order is already enqueued
     if (fork) cudaEventDestroy(fork);
-    for (int k = 0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
+    for (int k = K0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
     if (!rc) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = set_err(1000 + (int)e, "look-ahead enqueue failed: %s", cudaGetErrorString(e));
     }
     return rc;
+}
+
+// largest row count the resident 32-column panel kernel can take on this device (slab of rows in shared memory)
+static int64_t narrow_panel_max_rows(const dhqr_context* c) {
+    const int gmax = std::min(c->sms, PANEL_MAXG);
+    const int64_t rpc = ((184 * 1024) / (IB * 8) - 4) & ~(int64_t)7;
+    return rpc * gmax;
 }
 
 static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, int64_t col0, int64_t nl, double* A,
@@ -655,9 +776,34 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
     std::vector<Panel> panels;
     build_panels(col0s, nls, nb, panels);
     if (panels.empty()) return 0;
-    if (c->lookahead && panels.size() > 1 && !c->sync && !c->profile)
-        return qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels);
-    return qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels);
+    // rank-uniform precondition, checked on every rank BEFORE the first collective: a panel that neither chain can take
+    // would otherwise fail on its owner only and leave the other ranks inside ncclBroadcast
+    Plan pl = {0, 0, nb};
+    for (int k = 0; k < (int)panels.size(); ++k)
+        if (m - panels[k].c > narrow_panel_max_rows(c))
+            return set_err(-2, "m too large for the resident panel kernel (%lld rows; limit %lld)", (long long)(m - panels[k].c),
+                           (long long)narrow_panel_max_rows(c));
+    const bool la = c->lookahead && panels.size() > 1 && !c->sync && !c->profile;
+    for (;;) {
+        bool any_wide = false;
+        for (int k = pl.kstart; k < (int)panels.size(); ++k) any_wide |= plan_wide(c, pl, panels, k, m);
+        k_wide_reset<<<1, 32, 0, st>>>(c->wctl);
+        TRY(post(c, st, "k_wide_reset"));
+        const int rc = la && (int)panels.size() - pl.kstart > 1 ? qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels, pl)
+                                                                : qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels, pl);
+        if (rc || !any_wide) return rc;
+        // The wide chain is speculative: its guards are evaluated on the device.  One synchronisation per factorisation to
+        // learn whether a panel was refused; if so, everything from that panel on was skipped on the device and is redone
+        // here, that panel with the 32-column chain (same result on every rank: the verdict travels with the V buffer).
+        int fail = W_NOFAIL;
+        CU(cudaMemcpyAsync(&fail, &c->wctl->fail_step, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (fail == W_NOFAIL) return 0;
+        if (fail < pl.kstart || fail >= (int)panels.size()) return set_err(4004, "internal: bad restart index %d", fail);
+        c->wide_redone++;
+        pl.kstart = fail;
+        pl.wide_from = fail + 1;
+    }
 }
 
 // qr!: unblocked driver (nb == 1): one reflector per step, as the reference does it (S:127-144)
@@ -809,6 +955,7 @@ int dhqr_destroy(dhqr_handle c) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
+    cudaFree(c->wctl); cudaFree(c->wbuf);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
@@ -854,6 +1001,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->vta_max_chunks = (int)value;
     } else if (!strcmp(key, "panel_fast")) {
         c->panel_fast = value ? 1 : 0;
+    } else if (!strcmp(key, "wide_panel")) {
+        c->wide_panel = value ? 1 : 0;
     } else if (!strcmp(key, "panel_levels")) {
         if (value != 1 && value != 2) return set_err(-3, "panel_levels must be 1 or 2");
         c->panel_levels = (int)value;
@@ -883,6 +1032,9 @@ int dhqr_get_option(dhqr_handle c, const char* key, int64_t* value) {
     else if (!strcmp(key, "profile")) *value = c->profile;
     else if (!strcmp(key, "lookahead")) *value = c->lookahead;
     else if (!strcmp(key, "panel_fast")) *value = c->panel_fast;
+    else if (!strcmp(key, "wide_panel")) *value = c->wide_panel;
+    else if (!strcmp(key, "wide_panels")) *value = c->wide_panels;
+    else if (!strcmp(key, "wide_redone")) *value = c->wide_redone;
     else if (!strcmp(key, "panel_variant")) *value = PANEL_VARIANT;
     else if (!strcmp(key, "panels_fast") || !strcmp(key, "panels_fallback")) {
         int st2[2] = {0, 0};
@@ -1168,6 +1320,7 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     else if (!strcmp(which, "ypk")) { src = c->ws[0].ypk; have = c->ws[0].ypk_elems; }
     else if (!strcmp(which, "linv")) { src = c->ws[0].linv; have = (size_t)NBMAX * NBMAX; }
     else if (!strcmp(which, "vpk")) { src = c->vpk2[0]; have = c->vpk_elems[0]; }
+    else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)5 * WP * WP + 2 * XL_ELEMS : 0; }
     else if (!strcmp(which, "panel_trace")) { src = (const double*)c->panel_trace; have = c->panel_trace ? (size_t)PANEL_MAXG * IB * 8 : 0; }
     else return set_err(-2, "unknown buffer '%s'", which);
     if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);
@@ -1186,6 +1339,27 @@ int dhqr_k_panel_f64(dhqr_handle c, int64_t rows, int ncols, double* dP, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(c, rows, ncols));
     return launch_panel(c, st, c->vpk2[0], dP, ldp, rows, ncols, d_alpha, 0, 0, rup(rows, 128));
+}
+
+int dhqr_k_wide_panel_f64(dhqr_handle c, int64_t rows, double* dP, int64_t ldp, double* d_alpha, int* refused, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (rows < WP) return set_err(-2, "rows < 128");
+    if (!dP) return set_err(-3, "null panel");
+    if (ldp < rows) return set_err(-4, "ldp < rows");
+    if (!d_alpha) return set_err(-5, "null alpha");
+    if (!refused) return set_err(-6, "null result");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(c, rows, WP));
+    k_wide_reset<<<1, 32, 0, st>>>(c->wctl);
+    TRY(post(c, st, "k_wide_reset"));
+    const Panel p = {0, 0, WP};
+    TRY(factor_outer_panel(c, st, c->vpk2[0], c->ws[0], p, rows, 0, dP, ldp, d_alpha, 0, true));
+    WideCtl host;
+    CU(cudaMemcpyAsync(&host, c->wctl, sizeof(host), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *refused = host.status != 0 || host.fail_step != W_NOFAIL;
+    return 0;
 }
 
 }  // extern "C"

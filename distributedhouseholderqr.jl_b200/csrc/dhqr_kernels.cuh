@@ -29,6 +29,19 @@ constexpr int PANEL_VARIANT = DHQR_PANEL_VARIANT;
 // ~5e-18 x spread in ||QR - A|| / ||A|| (tests/test_fastpath_model.py), so they only take panels with a spread below 250.
 constexpr double FAST_SPREAD_MIN = (PANEL_VARIANT & 4) ? 4e-3 : 1e-5;
 
+// Control words of the speculative 128-column panel chain (dhqr_wide.cuh).  fail_step = index of the first outer panel whose
+// guards refused the fast factorisation (W_NOFAIL: none); every kernel that writes the caller's matrix carries a `gate` and
+// returns at once when a panel with an index below its gate has failed, so that the driver can redo the factorisation from
+// that panel on an untouched trailing matrix.
+constexpr int W_NOFAIL = 0x7fffffff;
+struct WideCtl {
+    int fail_step;
+    int status;      // guards of the panel in flight: 0 = fine
+};
+__device__ __forceinline__ bool wide_gate_closed(const WideCtl* ctl, int gate) {
+    return ctl && *reinterpret_cast<const volatile int*>(&ctl->fail_step) < gate;
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier, TMA bulk copy, fp64 tensor-core MMA
 // ------------------------------------------------------------------------------------------------
@@ -293,6 +306,8 @@ struct GemmCvyArgs {
     unsigned int* sm_ticket;   // [#SMs] ever-increasing per-SM counters (phase staggering), may be null
     int first_wave;     // CTAs with a linear id below this are in the first wave
     int stagger_cycles; // delay of the odd-ticket CTA of an SM in the first wave
+    const WideCtl* ctl; // speculative panel chain: skip when a panel below `gate` was refused (may be null)
+    int gate;
 };
 
 template <int WM, int MINB>
@@ -313,6 +328,7 @@ __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArg
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int nit = a.nkq;
+    if (wide_gate_closed(a.ctl, a.gate)) return;
 
     // The two CTAs that share an SM start together and would stay phase-locked (both loading C, both
     // in the MMA loop, both storing): delay one of each first-wave pair by about half a tile so that
@@ -608,6 +624,8 @@ struct PanelArgs {
     int* fast_stats;      // optional [2]: number of panels done by the fast path / by the column-wise fallback
     int levels;           // 2: owner warp gathers the partials and publishes a total; 1: every CTA gathers all partials itself
     long long* trace;     // optional clock64() stamps [gridDim.x][IB][8] (debugging / tuning); null = off
+    const WideCtl* ctl;   // speculative panel chain: skip when a panel below `gate` was refused (may be null)
+    int gate;
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long* cell, double v, uint32_t tag) {
@@ -643,6 +661,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
+    if (wide_gate_closed(a.ctl, a.gate)) return;   // grid-uniform: every CTA reads the same word before any exchange
     const int64_t row0 = (int64_t)cta * a.rows_per_cta;
     const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - row0));
     const int lds = a.lds, nc = a.ncols;

@@ -14,8 +14,14 @@
  *   - matrices are column-major double with leading dimension lda >= m (Julia Matrix /
  *     localpart(DArray)).  Device pointers unless the name says _host_.
  *   - stream-ordered: work is enqueued on the caller's cudaStream_t (passed as void*; NULL =
- *     legacy default stream) and the call returns without synchronising, except the _host_
- *     entry points, which block until their result is in host memory.
+ *     legacy default stream).  Synchronisation points, all of them: (i) the _host_ entry points block
+ *     until their result is in host memory; (ii) dhqr_qr_f64 with the default blocked path synchronises
+ *     the stream ONCE before returning whenever a panel went through the speculative 128-column chain
+ *     (option "wide_panel", on by default: its conditioning guards are evaluated on the device and a
+ *     refused panel is redone by the 32-column chain); (iii) with nranks > 1 every qr / apply_qt /
+ *     backsolve call exchanges the column partition first (one small all-gather + stream sync);
+ *     (iv) workspace growth (first call, or a larger problem than any before) allocates device memory.
+ *     Everything else returns without synchronising.
  *   - no pointer to caller memory is retained after return; workspace lives in the handle.
  *   - a handle is not thread-safe and its calls share one workspace: one handle per host thread, and
  *     consecutive calls on one handle must be on the same stream or ordered by the caller (events);
@@ -59,6 +65,9 @@ int dhqr_destroy(dhqr_handle h);
 /* Tunables (dhqr_set_option / dhqr_get_option):
  *   "nb"          outer panel width, multiple of 32 in [32,128] (default 128)
  *   "lookahead"   1 (default): panel chain on a high-priority stream ahead of the bulk update; 0: one stream, serial
+ *   "wide_panel"  1 (default): full, 32-aligned outer panels of width 128 are factored by the 128-column chain
+ *                 (CholeskyQR2 + Householder reconstruction on the whole panel: 3 grid-wide reductions per 128 columns,
+ *                 no cooperative launch); refused panels and all other panels use the 32-column chain below
  *   "panel_fast"  1 (default): inner panels by CholeskyQR2 + Householder reconstruction with on-device fallback
  *                 to the column-by-column kernel; 0: always column by column
  *   "panel_ctas"  CTAs of the cooperative panel kernel (0 = default: 64 under look-ahead, one per SM otherwise)
@@ -66,6 +75,7 @@ int dhqr_destroy(dhqr_handle h);
  *   "sync"        1: cudaStreamSynchronize + error check after every kernel launch (debugging; implies serial)
  *   "profile"     1: CUDA-event bracket per launch (implies serial), read with dhqr_profile_get
  *   read-only:    "sms", "rank", "nranks", "panels_fast", "panels_fallback" (inner panels taken by either path),
+ *                 "wide_panels" (outer panels factored by the 128-column chain), "wide_redone" (restarts after a refusal),
  *                 "panel_variant" (compile-time DHQR_PANEL_VARIANT of the panel kernel's fast path)
  *   experiment knobs kept for tools/: "panel_levels", "panel_backoff", "panel_trace", "la_trace", "vta_max_chunks",
  *                 "hp_max_ctas", "hp_priority", "cvy_stagger" */
@@ -139,6 +149,12 @@ int dhqr_debug_copy_f64(dhqr_handle h, const char *which, double *d_dst, int64_t
  * S:127-135 + S:208-209 restricted to the panel), alpha -> d_alpha[0:ncols]. */
 int dhqr_k_panel_f64(dhqr_handle h, int64_t rows, int ncols, double *dP, int64_t ldp, double *d_alpha,
                      void *stream);
+
+/* 128-column panel chain (CholeskyQR2 + Householder reconstruction, dhqr_wide.cuh): factor the rows x 128 panel at dP in
+ * place (same output as 128 steps of S:127-135 + S:208-209 restricted to the panel), alpha -> d_alpha[0:128].
+ * *refused = 1 when the on-device guards turned the panel down (dP is then untouched).  Synchronises `stream`. */
+int dhqr_k_wide_panel_f64(dhqr_handle h, int64_t rows, double *dP, int64_t ldp, double *d_alpha, int *refused,
+                          void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,82 @@
+"""CPU pin of the 128-column panel chain's algorithm (tests/widepanel_model.py restates the kernels stage by stage):
+same reflectors as the reference's column recurrences (S:127-135, S:198-213), residual at rounding level for every panel the
+guards accept, ill-conditioned / rank-deficient / non-finite panels refused, guards invariant under column scaling."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import widepanel_model as W   # noqa: E402
+
+
+def colres(oracle, P, H, a):
+    R = oracle.reconstruct(np.asfortranarray(H), a) - P
+    return float((np.linalg.norm(R, axis=0) / np.linalg.norm(P, axis=0)).max())
+
+
+@pytest.mark.parametrize("m", [128, 130, 256, 1024, 4096])
+def test_same_reflectors_as_the_reference_recurrences(oracle, m):
+    P = oracle.np_uniform(3, m, 128)
+    H, a, ok = W.wide_panel(P)
+    assert ok
+    Hr, ar = oracle.np_qr(P)
+    assert np.abs(H - Hr).max() < 1e-12
+    assert np.abs(a - ar).max() < 1e-13 * np.abs(ar).max()
+    assert oracle.qr_residual(P, np.asfortranarray(H), a) < 3e-15
+    V = np.tril(H)
+    assert np.abs((V * V).sum(0) - 2.0).max() < 1e-13            # |v|^2 = 2 (S:131-135)
+
+
+def test_blocked_sweep_matches_oracle(oracle):
+    A = oracle.np_uniform(0, 1100, 1024)
+    H, a, bad = W.blocked_qr(A)
+    assert bad < 0
+    Hr, ar = oracle.np_qr(A)
+    assert np.abs(H - Hr).max() < 1e-11
+    assert np.abs(a - ar).max() < 1e-12 * np.abs(ar).max()
+    assert oracle.qr_residual(A, np.asfortranarray(H), a) < 5e-15
+
+
+@pytest.mark.parametrize("kappa", [1e2, 1e4, 1e6, 1e7, 1e8, 1e10, 1e14])
+@pytest.mark.parametrize("scaled", [False, True])
+def test_guards(oracle, kappa, scaled):
+    rng = np.random.default_rng(5)
+    m, n = 1024, 128
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    Vt, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    P = (U * np.logspace(0, -np.log10(kappa), n)) @ Vt.T
+    if scaled:
+        P = P * np.logspace(-6, 6, n)[None, :]
+    H, a, ok = W.wide_panel(P)
+    if kappa <= 1e6:
+        assert ok                                                  # no cliff from column scaling
+    if kappa >= 1e8:
+        assert not ok
+    if ok:
+        assert colres(oracle, P, H, a) < 5e-14                     # every accepted panel is backward stable, column by column
+
+
+def test_degenerate_panels_are_refused():
+    P = np.random.default_rng(0).random((512, 128))
+    for bad in ("zero", "dup", "nan", "inf"):
+        Q = P.copy()
+        if bad == "zero":
+            Q[:, 17] = 0.0
+        elif bad == "dup":
+            Q[:, 40] = Q[:, 3]
+        elif bad == "nan":
+            Q[100, 5] = np.nan
+        else:
+            Q[7, 99] = np.inf
+        with np.errstate(all="ignore"):
+            assert not W.wide_panel(Q)[2]
+
+
+def test_explicit_inverse_by_doubling():
+    rng = np.random.default_rng(1)
+    R = np.triu(rng.standard_normal((128, 128))) + 12 * np.eye(128)
+    X = W.triu_inverse(R)
+    assert np.abs(X @ R - np.eye(128)).max() < 1e-14
+    assert np.abs(np.tril(X, -1)).max() == 0.0
