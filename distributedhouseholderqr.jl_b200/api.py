@@ -328,16 +328,50 @@ def solve_householder_(b: torch.Tensor, A, alpha: torch.Tensor, handle: Optional
     return b[:n]
 
 
-def apply_qt_(b: torch.Tensor, A, handle: Optional[Handle] = None) -> torch.Tensor:
-    """_solve_householder1! (S:226-242): b <- H_n ... H_1 b."""
+def _rhs_args(b: torch.Tensor, m: int):
+    if b.dtype != torch.float64:
+        raise TypeError("b must be float64")
+    if b.dim() not in (1, 2) or b.shape[0] != m:
+        raise ValueError(f"b must have {m} rows (a length-m vector or an (m, k) column-major block)")
+    if b.dim() == 1:
+        if not b.is_contiguous():
+            raise ValueError("b must be contiguous")
+        return max(m, 1), 1
+    return _lda(b), b.shape[1]
+
+
+def _apply(fn: str, b: torch.Tensor, A, handle: Optional[Handle]) -> torch.Tensor:
     loc, n, col0, h = _dev_args(A)
     h = handle or h
     m = loc.shape[0]
-    ldb, nrhs = (max(m, 1), 1) if b.dim() == 1 else (_lda(b), b.shape[1])
+    ldb, nrhs = _rhs_args(b, m)
     with torch.cuda.device(loc.device):
-        _lib.call("dhqr_apply_qt_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+        _lib.call(fn, h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
                   C.c_void_p(b.data_ptr()), ldb, nrhs, _stream_ptr(loc.device))
     return b
+
+
+def apply_qt_(b: torch.Tensor, A, handle: Optional[Handle] = None) -> torch.Tensor:
+    """_solve_householder1! (S:226-242): b <- H_n ... H_1 b = Q'b, in place (b: length m, or (m, k) column-major)."""
+    return _apply("dhqr_apply_qt_f64", b, A, handle)
+
+
+def apply_q_(b: torch.Tensor, A, handle: Optional[Handle] = None) -> torch.Tensor:
+    """b <- H_1 ... H_n b = Q b, in place: the inverse of apply_qt_ (the reference never forms Q; this exposes the
+    factorisation as an operator)."""
+    return _apply("dhqr_apply_q_f64", b, A, handle)
+
+
+def backsolve_(b: torch.Tensor, A, alpha: torch.Tensor, handle: Optional[Handle] = None) -> torch.Tensor:
+    """_solve_householder2! (S:256-282): b[0:n] <- R^{-1} b[0:n] with R = triu(A,1) + diag(alpha); returns b[0:n]."""
+    loc, n, col0, h = _dev_args(A)
+    h = handle or h
+    m = loc.shape[0]
+    ldb, nrhs = _rhs_args(b, m)
+    with torch.cuda.device(loc.device):
+        _lib.call("dhqr_backsolve_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+                  C.c_void_p(alpha.data_ptr()), C.c_void_p(b.data_ptr()), ldb, nrhs, _stream_ptr(loc.device))
+    return b[:n]
 
 
 def ldiv(H: DistributedHouseholderQRStruct, b):
@@ -345,6 +379,8 @@ def ldiv(H: DistributedHouseholderQRStruct, b):
     if isinstance(H.A, np.ndarray):
         m, n = H.A.shape
         bb = np.ascontiguousarray(b, dtype=np.float64)
+        if bb.ndim != 1 or bb.shape[0] != m:
+            raise ValueError(f"b must be a length-{m} vector")
         x = np.zeros(n)
         _lib.call("dhqr_ldiv_host_f64", H.handle.raw, m, n, C.c_void_p(H.A.ctypes.data), max(H.A.strides[1] // 8, 1),
                   C.c_void_p(H.α.ctypes.data), C.c_void_p(bb.ctypes.data), C.c_void_p(x.ctypes.data))

@@ -139,6 +139,9 @@ struct dhqr_context {
     WideCtl* wctl = nullptr;                                            // device control words (first refused panel, guards of the panel in flight)
     double* wbuf = nullptr;                                             // R1, R2, X2, Rt, Y3 (plain 128x128) + XL, XL3 (rmul operand layout)
     int64_t wide_panels = 0, wide_redone = 0;                           // statistics: panels factored by the wide chain / factorisations restarted
+    double wide_kappa = 1000.0;                                         // guard on ||D R1^{-1}||_F of the first Cholesky factor (option "wide_kappa")
+    long long* wstamps = nullptr;                                       // clock64 stamps of the single-CTA kernels (option "wide_trace")
+    int wide_trace = 0;
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
     double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
@@ -197,6 +200,7 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(k_chol128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_WIDE1));
     CU(cudaFuncSetAttribute(k_hr128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_WIDE1));
     CU(cudaFuncSetAttribute(k_vpk_rmul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_RMUL));
+    CU(cudaFuncSetAttribute(k_trimm128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIMM));
     CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->attrs_set = true;
     return 0;
@@ -250,6 +254,8 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         CU(cudaMemcpy(c->wctl, &init, sizeof(init), cudaMemcpyHostToDevice));
         size_t o3 = 0;
         TRY(ensure(&c->wbuf, &o3, (size_t)5 * WP * WP + 2 * XL_ELEMS));
+        CU(cudaMalloc((void**)&c->wstamps, 32 * sizeof(long long)));
+        CU(cudaMemset(c->wstamps, 0, 32 * sizeof(long long)));
     }
     TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
@@ -321,7 +327,7 @@ static int pick_splits(int tiles, int nchunks, int sms, int max_chunks, int64_t 
 //   Gram matrix; `w` = the workspace set of the calling chain.
 static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int voff, int nbp,
                                  int64_t rows, int64_t row_lo, double* C, int64_t ldc, int ncols, int max_chunks = 0,
-                                 bool reuse_T = false, double* linv_io = nullptr, int gate = 0) {
+                                 bool reuse_T = false, double* linv_io = nullptr, int gate = 0, int trans = 0) {
     double* linv = linv_io ? linv_io : w.linv;   // where T' is written (or read from, with reuse_T)
     // reuse_T: w.linv already holds T' of this V (same chain, previous call) -> skip the Gram block and k_tinv
     if (ncols <= 0 || rows <= 0) return 0;
@@ -353,7 +359,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     const int ygrid = (ncols + YCOLS - 1) / YCOLS;
     if (small && !reuse_T) {
         pre(c, st);
-        k_mid32<<<ygrid, 512, 0, st>>>(w.wpart, pstride, nsplit, ncols, w.ypk, linv);
+        k_mid32<<<ygrid, 512, 0, st>>>(w.wpart, pstride, nsplit, ncols, w.ypk, linv, trans);
         TRY(post(c, st, "k_mid32"));
     } else {
         pre(c, st);
@@ -367,8 +373,8 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
             TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
         }
         pre(c, st);
-        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, linv, w.ypk);
-        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, linv, w.ypk);
+        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans);
+        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans);
         TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
     }
     pre(c, st);
@@ -549,22 +555,23 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
     TRY(post(c, st, "k_pack"));
     TRY(wide_gram(c, st, vpk, w, g.rows));
     pre(c, st);
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, nullptr, XL, c->wctl, step, vflag);
+    long long* stamps = c->wide_trace ? c->wstamps : nullptr;
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, nullptr, XL, c->wctl, step, vflag, c->wide_kappa, stamps);
     TRY(post(c, st, "k_chol128"));
     TRY(rmul(0, nq, XL, nullptr));
     TRY(wide_gram(c, st, vpk, w, g.rows));
     pre(c, st);
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, X2, XL, c->wctl, step, vflag);
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, X2, XL, c->wctl, step, vflag, c->wide_kappa, stamps ? stamps + 8 : nullptr);
     TRY(post(c, st, "k_chol128"));
     pre(c, st);
-    k_trimm128<<<10, 256, 0, st>>>(R2, R1, Rt, nullptr, c->wctl, step);
+    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(R2, R1, Rt, nullptr, c->wctl, step);
     TRY(post(c, st, "k_trimm128"));
     TRY(rmul(0, 2, XL, nullptr));
     pre(c, st);
-    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Y3, c->wctl, step);
+    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Y3, c->wctl, step, stamps ? stamps + 16 : nullptr);
     TRY(post(c, st, "k_hr128"));
     pre(c, st);
-    k_trimm128<<<10, 256, 0, st>>>(X2, Y3, nullptr, XL3, c->wctl, step);
+    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(X2, Y3, nullptr, XL3, c->wctl, step);
     TRY(post(c, st, "k_trimm128"));
     TRY(rmul(2, nq - 2, XL3, P));
     c->wide_panels++;
@@ -853,8 +860,11 @@ static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, 
 // Q'b on the local reflectors: panels of <= 128 reflectors, each applied as a block reflector
 // built from V alone (T recomputed from V'V), so only (A, alpha) are needed, like the reference.
 static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, const double* A,
-                          int64_t lda, double* b, int64_t ldb, int nrhs) {
-    for (int64_t o = 0; o < nl; o += NBMAX) {
+                          int64_t lda, double* b, int64_t ldb, int nrhs, int notrans = 0) {
+    // notrans: b <- Q b = H_1 (H_2 (... H_n b)): the panels in reverse order, each as I - V T V' (T instead of T')
+    if (nl <= 0) return 0;
+    const int64_t ofirst = notrans ? ((nl - 1) / NBMAX) * NBMAX : 0, ostep = notrans ? -(int64_t)NBMAX : NBMAX;
+    for (int64_t o = ofirst; o >= 0 && o < nl; o += ostep) {
         const int kb = (int)std::min<int64_t>(NBMAX, nl - o);
         const int64_t cs = col0 + o;
         const int64_t r0 = cs & ~(int64_t)31;
@@ -863,7 +873,7 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
         dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbp);
         k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk2[0], 0, cs - r0, vrows);
         TRY(post(c, st, "k_pack"));
-        TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbp, rows, cs - r0, b + r0, ldb, nrhs));
+        TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbp, rows, cs - r0, b + r0, ldb, nrhs, 0, false, nullptr, 0, notrans));
     }
     return 0;
 }
@@ -955,7 +965,7 @@ int dhqr_destroy(dhqr_handle c) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
-    cudaFree(c->wctl); cudaFree(c->wbuf);
+    cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
@@ -1003,6 +1013,11 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->panel_fast = value ? 1 : 0;
     } else if (!strcmp(key, "wide_panel")) {
         c->wide_panel = value ? 1 : 0;
+    } else if (!strcmp(key, "wide_kappa")) {
+        if (value < 1) return set_err(-3, "wide_kappa < 1");
+        c->wide_kappa = (double)value;
+    } else if (!strcmp(key, "wide_trace")) {
+        c->wide_trace = value ? 1 : 0;
     } else if (!strcmp(key, "panel_levels")) {
         if (value != 1 && value != 2) return set_err(-3, "panel_levels must be 1 or 2");
         c->panel_levels = (int)value;
@@ -1121,6 +1136,30 @@ int dhqr_apply_qt_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, 
     if (c->nranks > 1) {
         if (c->rank + 1 < c->nranks) NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
         NC(g_nccl.Broadcast(d_b, d_b, cnt, ncclFloat64, c->nranks - 1, c->comm, st));
+    }
+    return 0;
+}
+
+int dhqr_apply_q_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const double* dA,
+                     int64_t lda, double* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(check_common(c, m, n_global, col0, n_local, dA, lda));
+    if (nrhs < 0) return set_err(-10, "nrhs < 0");
+    if (nrhs > 0 && !d_b) return set_err(-8, "null b");
+    if (ldb < std::max<int64_t>(1, m)) return set_err(-9, "ldb < max(1,m)");
+    if (n_global == 0 || nrhs == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> col0s, nls;
+    TRY(gather_partition(c, st, col0, n_local, col0s, nls));
+    TRY(check_partition(col0s, nls, n_global));
+    TRY(ensure_workspace(c, m, std::max<int64_t>(n_local, nrhs)));
+    // b <- H_1 ... H_n b: the owners act in reverse rank order, b travels rank -> rank - 1
+    const size_t cnt = (size_t)ldb * (nrhs - 1) + m;
+    if (c->nranks > 1 && c->rank + 1 < c->nranks) NC(g_nccl.Recv(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
+    TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs, 1));
+    if (c->nranks > 1) {
+        if (c->rank > 0) NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank - 1, c->comm, st));
+        NC(g_nccl.Broadcast(d_b, d_b, cnt, ncclFloat64, 0, c->comm, st));
     }
     return 0;
 }
@@ -1320,6 +1359,7 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     else if (!strcmp(which, "ypk")) { src = c->ws[0].ypk; have = c->ws[0].ypk_elems; }
     else if (!strcmp(which, "linv")) { src = c->ws[0].linv; have = (size_t)NBMAX * NBMAX; }
     else if (!strcmp(which, "vpk")) { src = c->vpk2[0]; have = c->vpk_elems[0]; }
+    else if (!strcmp(which, "wstamps")) { src = (const double*)c->wstamps; have = c->wstamps ? 32 : 0; }
     else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)5 * WP * WP + 2 * XL_ELEMS : 0; }
     else if (!strcmp(which, "panel_trace")) { src = (const double*)c->panel_trace; have = c->panel_trace ? (size_t)PANEL_MAXG * IB * 8 : 0; }
     else return set_err(-2, "unknown buffer '%s'", which);

@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, 
 // this CTA's 32 W columns (fixed order), T' = (I + stril(S))^{-1}, Y = -T'W in the packed ypk layout.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp, int64_t pstride, int nsplit, int na,
-                                                  double* __restrict__ ypk, double* __restrict__ linv_out) {
+                                                  double* __restrict__ ypk, double* __restrict__ linv_out, int trans) {
     constexpr int NBP = 32, LDL = 33;
     __shared__ double L[NBP * LDL];
     __shared__ double T[1024];
@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp,
     for (int h = 0; h < 2; ++h) {
         const int j = jg * 2 + h;
         double acc = 0.0;
-        for (int k = 0; k <= i; ++k) acc += L[k * LDL + i] * sW[j * NBP + k];
+        if (!trans) for (int k = 0; k <= i; ++k) acc += L[k * LDL + i] * sW[j * NBP + k];        // Y = -T' W  (Q' C)
+        else for (int k = i; k < NBP; ++k) acc += L[i * LDL + k] * sW[j * NBP + k];               // Y = -T W   (Q C)
         const int col = c0 + j;
         ypk[(int64_t)(col / YT) * (YT * LDK) + (col % YT) * LDK + i] = (col < na) ? -acc : 0.0;   // NKQ == 1
     }
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp,
 // ------------------------------------------------------------------------------------------------
 template <int NBP>
 __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int woff, int na, const double* __restrict__ Linv,
-                                                  double* __restrict__ ypk) {
+                                                  double* __restrict__ ypk, int trans) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sL = reinterpret_cast<double*>(smem_raw);   // [NBP][NBP] col-major
     double* sW = sL + NBP * NBP;                         // [YCOLS][NBP]
@@ -578,10 +579,18 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws,
     double acc[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[j] = 0.0;
-    for (int k = 0; k <= i; ++k) {            // Linv is lower triangular
-        const double l = sL[k * NBP + i];
+    if (!trans) {
+        for (int k = 0; k <= i; ++k) {            // Linv = T' is lower triangular: Y = -T' W (the block form of Q' C)
+            const double l = sL[k * NBP + i];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[j] += l * sW[(jh * CPT + j) * NBP + k];
+            for (int j = 0; j < CPT; ++j) acc[j] += l * sW[(jh * CPT + j) * NBP + k];
+        }
+    } else {
+        for (int k = i; k < NBP; ++k) {           // Y = -T W = -Linv' W (the block form of Q C)
+            const double l = sL[i * NBP + k];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] += l * sW[(jh * CPT + j) * NBP + k];
+        }
     }
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {

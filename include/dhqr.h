@@ -107,6 +107,10 @@ int dhqr_qr_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_
 int dhqr_apply_qt_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
                       const double *dA_local, int64_t lda, double *d_b, int64_t ldb, int nrhs,
                       void *stream);
+/* b <- Q b = H_1 ... H_n b: the inverse of the sweep above (not in the reference, which never forms Q; SURVEY 8f-3:
+ * exposes the factorisation as an operator, e.g. to form Q explicitly or to compute residuals b - A x = Q [0; (Q'b)[n:]]). */
+int dhqr_apply_q_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                     const double *dA_local, int64_t lda, double *d_b, int64_t ldb, int nrhs, void *stream);
 /* b[0:n] <- R^{-1} b[0:n]  (_solve_householder2! S:256-282 / S:244-254), R = triu(A,1)+diag(alpha). */
 int dhqr_backsolve_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
                        const double *dA_local, int64_t lda, const double *d_alpha, double *d_b,

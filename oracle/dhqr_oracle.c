@@ -169,6 +169,36 @@ int dhqr_oracle_qr_steps(int64_t m, int64_t n, double *a, int64_t lda, double *a
     return 0;
 }
 
+/* Strided bounded sample for bench.py: runs the genuine column step of S:127-144 (norm, alpha, scale, copy, trailing
+ * update of every column to the right) for j = j0, j0 + stride, j0 + 2 stride, ... < n on whatever the matrix holds.
+ * The arithmetic has no data-dependent control flow, so the cost of step j does not depend on the steps before it having
+ * run; sampling the whole sweep at a fixed stride covers the early (out-of-cache) and the late (cache-resident) steps in
+ * the proportion the full factorisation has them.  *flops = the flops of the sampled steps (counted exactly). */
+int dhqr_oracle_qr_steps_strided(int64_t m, int64_t n, double *a, int64_t lda, double *alpha, int64_t j0, int64_t stride,
+                                 int nthreads, double *flops) {
+    if (lda < (m > 1 ? m : 1)) return -4;
+    if (stride < 1 || j0 < 0) return -6;
+    if (nthreads < 1) nthreads = dhqr_oracle_max_threads();
+    dhqr_oracle_block b = {a, lda, 0, n};
+    double *hj = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+    if (!hj) return -100;
+    double fl = 0.0;
+    for (int64_t j = j0; j < n; j += stride) {
+        double *col = a + j * lda;
+        double s = nrm2(col + j, m - j);                           /* S:129 */
+        alpha[j] = s * dhqr_oracle_alphafactor(col[j]);            /* S:130 */
+        double f = 1.0 / sqrt(s * (s + fabs(col[j])));             /* S:131 */
+        col[j] -= alpha[j];                                        /* S:132 */
+        for (int64_t i = j; i < m; ++i) col[i] *= f;               /* S:133-135 */
+        memcpy(hj, col, (size_t)m * sizeof(double));               /* S:138-140 */
+        householder_inner(&b, m, n, j, hj, nthreads);              /* S:141-143 */
+        fl += 3.0 * (double)(m - j) + 4.0 * (double)(m - j) * (double)(n - j - 1);
+    }
+    free(hj);
+    if (flops) *flops = fl;
+    return 0;
+}
+
 /* S:232-242 (and the Vector twin S:215-224)  b <- H_n ... H_1 b = Q'b, owner by owner (S:227-229). */
 int dhqr_oracle_apply_qt_blocks(int64_t m, int64_t n, int nblocks, const dhqr_oracle_block *blocks,
                                 double *b) {

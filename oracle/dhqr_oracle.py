@@ -65,6 +65,7 @@ class COracle:
         L.dhqr_oracle_partialdot.argtypes = [vp, vp, i64, i64]
         L.dhqr_oracle_qr.argtypes = [i64, i64, vp, i64, vp, ci]
         L.dhqr_oracle_qr_steps.argtypes = [i64, i64, vp, i64, vp, i64, ci, C.POINTER(dbl)]
+        L.dhqr_oracle_qr_steps_strided.argtypes = [i64, i64, vp, i64, vp, i64, i64, ci, C.POINTER(dbl)]
         L.dhqr_oracle_householder_blocks.argtypes = [i64, i64, ci, C.POINTER(_Block), vp, ci]
         L.dhqr_oracle_apply_qt_blocks.argtypes = [i64, i64, ci, C.POINTER(_Block), vp]
         L.dhqr_oracle_backsolve_blocks.argtypes = [i64, i64, ci, C.POINTER(_Block), vp, vp]
@@ -112,6 +113,18 @@ class COracle:
         rc = self.lib.dhqr_oracle_qr_steps(m, n, _fptr(a), a.strides[1] // 8, _fptr(alpha), jstop, nthreads, C.byref(fl))
         if rc:
             raise RuntimeError(f"dhqr_oracle_qr_steps rc={rc}")
+        return alpha, fl.value
+
+    def qr_steps_strided(self, a: np.ndarray, j0: int, stride: int, nthreads: int = 0):
+        """Column steps j0, j0+stride, ... of S:127-144 on the current contents of ``a`` (bench.py's bounded sample)."""
+        _check_colmajor(a)
+        m, n = a.shape
+        alpha = np.zeros(n)
+        fl = C.c_double(0.0)
+        rc = self.lib.dhqr_oracle_qr_steps_strided(m, n, _fptr(a), a.strides[1] // 8, _fptr(alpha), j0, stride, nthreads,
+                                                   C.byref(fl))
+        if rc:
+            raise RuntimeError(f"dhqr_oracle_qr_steps_strided rc={rc}")
         return alpha, fl.value
 
     @staticmethod

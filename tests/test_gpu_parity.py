@@ -188,6 +188,36 @@ def test_multiple_right_hand_sides(D, dev, oracle, coracle):
         assert np.abs(X[:, j] - xr).max() < 1e-9 * np.abs(xr).max()
 
 
+def test_apply_q_is_the_inverse_sweep(D, dev, oracle, coracle):
+    # Q b = H_1 ... H_n b (the factorisation as an operator): inverts apply_qt_, reproduces A = Q R column by
+    # column, and matches the numpy sweep of the oracle's reflectors
+    for m, n in [(300, 37), (1100, 1000), (4096, 640)]:
+        A0 = coracle.fill_uniform(6, m, n)
+        Href = A0.copy(order="F")
+        Href, aref = coracle.qr(Href)
+        A = D.to_colmajor(A0, dev)
+        H = D.qr_(A)
+        B0 = oracle.np_uniform(7, m, 3)
+        B = D.to_colmajor(B0, dev)
+        D.apply_qt_(B, A)
+        D.apply_q_(B, A)
+        assert np.abs(B.cpu().numpy() - B0).max() < 1e-12 * np.abs(B0).max() * np.sqrt(m)
+        b = B0[:, 0].copy()
+        w = b.copy()
+        for j in range(n - 1, -1, -1):                                   # H_1 (H_2 (... H_n b))
+            v = Href[j:, j]
+            w[j:] -= v * (v @ w[j:])
+        qb = D.apply_q_(torch.from_numpy(b).to(dev), A).cpu().numpy()
+        assert np.linalg.norm(qb - w) < TOL_QTB * np.linalg.norm(b)
+        R = torch.zeros(m, 4, dtype=torch.float64)
+        cols = [0, 1, n // 2, n - 1]
+        for q, c in enumerate(cols):
+            R[:c, q] = torch.from_numpy(Href[:c, c])
+            R[c, q] = aref[c]
+        QR = D.apply_q_(D.to_colmajor(R, dev), A).cpu().numpy()
+        assert np.abs(QR - A0[:, cols]).max() < 1e-12 * np.sqrt(m)
+
+
 def test_bitwise_determinism(D, dev):
     # fixed-order reductions everywhere: two runs must agree bit for bit (this is what exposed the TMA WAR race)
     outs = []
@@ -336,7 +366,7 @@ def test_aliasing_and_repeatable_solve(D, dev, oracle):
 
 # ---- BASELINE's full sizes through size-independent properties -------------------------------------
 @pytest.mark.parametrize("mn", [(32768, 4096)])
-def test_full_size_properties(D, dev, mn):
+def test_full_size_properties(D, dev, coracle, mn):
     m, n = mn
     A0 = D.colmajor_empty(m, n, dev)
     D.fill_uniform_(A0, 0)
@@ -355,6 +385,18 @@ def test_full_size_properties(D, dev, mn):
     x_ref = torch.linalg.lstsq(A0, b.unsqueeze(1)).solution[:, 0]
     r_ref = A0.T @ (A0 @ x_ref) - A0.T @ b
     assert float(torch.linalg.norm(r)) < 8 * float(torch.linalg.norm(r_ref))   # T:62 with cuSOLVER as "stdlib"
+    # H[:, :k] and alpha[:k] depend on A[:, :k] only: the C oracle on the leading 256 columns pins the full-size run
+    k = 256
+    Hk = coracle.fill_uniform(0, m, k)
+    Hk, ak = coracle.qr(Hk)
+    assert np.abs(A[:, :k].cpu().numpy() - Hk).max() < TOL_H
+    assert np.abs(H.α[:k].cpu().numpy() - ak).max() < TOL_A * np.abs(ak).max()
+    # LAPACK (cuSOLVER geqrf) at full size through the storage-format identity alpha = diag(R), triu(H,1) = triu(R,1)
+    Rl = torch.geqrf(A0)[0]
+    scale = float(Rl[:n].abs().max())
+    assert float((torch.diagonal(Rl[:n]) - H.α).abs().max()) < 1e-11 * scale
+    assert float((torch.triu(Rl[:n], 1) - torch.triu(A[:n], 1)).abs().max()) < 1e-10 * scale
+    del Rl
     # unblocked and blocked paths agree (linearity of the algorithm in storage): compare alpha on a slice
     A2 = A0[:, :256].clone()
     A3 = D.colmajor_empty(m, 256, dev)

@@ -39,23 +39,48 @@ def test_blocked_sweep_matches_oracle(oracle):
     assert oracle.qr_residual(A, np.asfortranarray(H), a) < 5e-15
 
 
-@pytest.mark.parametrize("kappa", [1e2, 1e4, 1e6, 1e7, 1e8, 1e10, 1e14])
-@pytest.mark.parametrize("scaled", [False, True])
-def test_guards(oracle, kappa, scaled):
+def ill_conditioned_panels(oracle):
     rng = np.random.default_rng(5)
     m, n = 1024, 128
     U, _ = np.linalg.qr(rng.standard_normal((m, n)))
     Vt, _ = np.linalg.qr(rng.standard_normal((n, n)))
-    P = (U * np.logspace(0, -np.log10(kappa), n)) @ Vt.T
-    if scaled:
-        P = P * np.logspace(-6, 6, n)[None, :]
-    H, a, ok = W.wide_panel(P)
-    if kappa <= 1e6:
-        assert ok                                                  # no cliff from column scaling
-    if kappa >= 1e8:
-        assert not ok
-    if ok:
-        assert colres(oracle, P, H, a) < 5e-14                     # every accepted panel is backward stable, column by column
+    P0 = oracle.np_uniform(8, m, n)
+    for kappa in (1e1, 1e2, 1e3, 1e4, 1e6, 1e8, 1e12):
+        yield f"geo{kappa:.0e}", (U * np.logspace(0, -np.log10(kappa), n)) @ Vt.T
+        yield f"one{kappa:.0e}", (U * np.r_[np.ones(n - 1), 1.0 / kappa]) @ Vt.T
+    for eps in (1e-1, 1e-2, 1e-3, 1e-4, 1e-6, 1e-9):       # two nearly identical columns on top of the rank-one mean of U[0,1)
+        for c in (9, 99):
+            Q = P0.copy()
+            Q[:, c] = Q[:, 2] + eps * oracle.np_uniform(10, m, 1)[:, 0]
+            yield f"dup{c}_{eps:.0e}", Q
+
+
+def test_guards_keep_every_accepted_panel_backward_stable(oracle):
+    accepted = 0
+    for name, P in ill_conditioned_panels(oracle):
+        for scaled in (False, True):
+            Q = P * np.logspace(-6, 6, 128)[None, :] if scaled else P
+            H, a, ok = W.wide_panel(Q)
+            H1, a1, ok1 = W.wide_panel(P)
+            assert ok == ok1, name                                     # the guards are invariant under column scaling
+            if ok:
+                accepted += 1
+                assert colres(oracle, Q, H, a) < 5e-14, name           # column by column, not just in the Frobenius norm
+    assert accepted >= 12                                              # ... and they do not refuse everything
+    for name, P in ill_conditioned_panels(oracle):                     # well-conditioned panels must pass
+        if name in ("geo1e+01", "one1e+01", "geo1e+02", "dup9_1e-01", "dup99_1e-01", "dup9_1e-02"):
+            assert W.wide_panel(P)[2], name
+        if name.endswith("1e+12") or name.endswith("1e-09"):
+            assert not W.wide_panel(P)[2], name
+
+
+def test_what_the_conditioning_guard_protects_against(oracle):
+    # without the guard on ||D R1^{-1}||_F the explicit inverse loses accuracy in proportion to that number
+    P = oracle.np_uniform(8, 1024, 128)
+    P[:, 9] = P[:, 2] + 1e-5 * oracle.np_uniform(10, 1024, 1)[:, 0]
+    assert not W.wide_panel(P)[2]
+    H, a, ok = W.wide_panel(P, kappa_max=1e30)
+    assert ok and oracle.qr_residual(P, np.asfortranarray(H), a) > 1e-13
 
 
 def test_degenerate_panels_are_refused():

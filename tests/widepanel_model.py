@@ -16,6 +16,8 @@ import numpy as np
 
 NB = 128
 ORTH_MAX = 0.25          # guard on ||Q1'Q1 - I||: max-norm <= ORTH_MAX / nb  =>  2-norm <= 1/4
+KAPPA_MAX = 1.0e3        # guard on ||D R1^{-1}||_F, D = diag(||p_j||): multiplying by the EXPLICIT inverse (a GEMM on the tensor
+                         # pipe instead of a substitution) costs ~1e-17 x that number in ||QR - A|| / ||A|| (measured below)
 
 
 def cholesky_upper(G):
@@ -62,6 +64,12 @@ def triu_inverse(R, base=8):
     return X
 
 
+def kappa_estimate(R, X):
+    """||D X||_F with D = diag(column norms of R) = diag(||p_j||): invariant under column scaling of the panel."""
+    d = np.sqrt((R * R).sum(0))
+    return float(np.sqrt(((d[:, None] * X) ** 2).sum()))
+
+
 def signed_lu(W):
     """LU of the top block of E - Q S with S_j = -sign(pivot) chosen on the fly; returns (Wt, Sg, Ud):
     strict upper part of Wt = frozen rows U, strict lower part = W_ij^(j)."""
@@ -77,10 +85,10 @@ def signed_lu(W):
     return Wt, Sg, Ud
 
 
-def wide_panel(P):
+def wide_panel(P, kappa_max=KAPPA_MAX):
     """Returns (H, alpha, ok): H in the reference's storage; ok False when a guard refuses the panel (non-positive or
-    non-finite Cholesky pivot, or the first pass left ||Q1'Q1 - I|| > 1/4) — the driver then redoes the panel with the
-    32-column chain.  The guards are invariant under column scaling (CholeskyQR2 and the explicit inverses are)."""
+    non-finite Cholesky pivot, ||D R1^{-1}||_F > kappa_max, or the first pass left ||Q1'Q1 - I|| > 1/4) — the driver then
+    redoes the panel with the 32-column chain.  The guards are invariant under column scaling."""
     P = np.array(P, dtype=np.float64)
     m, n = P.shape
     assert m >= n
@@ -88,6 +96,8 @@ def wide_panel(P):
     if not ok:
         return None, None, False
     X1 = triu_inverse(R1)
+    if not (kappa_estimate(R1, X1) <= kappa_max):
+        return None, None, False
     Q1 = P @ X1
     G2 = Q1.T @ Q1
     if not np.all(np.abs(G2 - np.eye(n)) <= ORTH_MAX / n):

@@ -33,7 +33,14 @@ def timeline(tag):
     dp = np.diff(np.concatenate([[0], t[:, 0]])); db = np.diff(np.concatenate([[0], t[:, 2]]))
     print(tag, "timeline total %.2f ms; panel steps:" % t[-1].max(), np.round(dp, 2).tolist(), flush=True)
     print(tag, "          bulk steps:", np.round(db, 2).tolist(), flush=True)
+def stamps(tag):
+    h.set_option("wide_trace", 1); D.fill_uniform_(A, 0); D.householder_(A, al, 0); torch.cuda.synchronize(); h.set_option("wide_trace", 0)
+    buf = torch.zeros(32, dtype=torch.float64, device=dev)
+    D._lib.call("dhqr_debug_copy_f64", h.raw, b"wstamps", C.c_void_p(buf.data_ptr()), 32, None); torch.cuda.synchronize()
+    s = buf.cpu().numpy().view(np.int64)
+    print(tag, "clock64 stamps of the last panel (cycles): chol1 [load+guard, factor, inverse, outputs]", s[0:4].tolist(), "chol2", s[8:12].tolist(), "hr128 [load, LU, top block + Rr inverse]", s[20:23].tolist(), flush=True)
 show("default (wide)")
+stamps("wide")
 print("wide panels / redone:", h.get_option("wide_panels"), h.get_option("wide_redone"))
 profile("wide"); timeline("wide")
 h.set_option("lookahead", 0); show("wide serial"); h.set_option("lookahead", 1)
