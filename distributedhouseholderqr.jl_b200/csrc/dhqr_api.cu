@@ -127,6 +127,7 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
+    int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
     int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     int tail_cols = 0;                                                  // trailing width below which the chain is considered critical
     int wide_panel_ctas = 64;                                           // panel CTAs while the bulk update is wide
@@ -181,8 +182,9 @@ static size_t smem_ymake(int nbp) { return ((size_t)nbp * nbp + YCOLS * nbp) * 8
 
 #define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_NPW>
 #define K_G1_32 k_gemm_vta<32, G1S_BN, 1, 4, G1S_NPW>
-#define K_G2 k_gemm_cvy<2, 2>
-#define K_G2W k_gemm_cvy<4, 2>
+#define K_G2 k_gemm_cvy<2, 2, false>
+#define K_G2W k_gemm_cvy<4, 2, false>
+#define K_G2D k_gemm_cvy<4, 2, true>
 
 static int set_attrs(dhqr_context* c) {
     if (c->attrs_set) return 0;
@@ -192,6 +194,8 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(K_G2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
+    CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
     CU(cudaFuncSetAttribute(k_tinv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(32)));
     CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
@@ -201,6 +205,7 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(k_hr128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_WIDE1));
     CU(cudaFuncSetAttribute(k_vpk_rmul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_RMUL));
     CU(cudaFuncSetAttribute(k_trimm128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIMM));
+    CU(cudaFuncSetAttribute(k_trimm_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIMM));
     CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->attrs_set = true;
     return 0;
@@ -250,10 +255,10 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
     if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)IB * (PANEL_MAXG + 2) * IB * 2)); c->ll_epoch = 0; }
     if (!c->wctl) {
         CU(cudaMalloc((void**)&c->wctl, sizeof(WideCtl)));
-        const WideCtl init = {W_NOFAIL, 0};
+        const WideCtl init = {W_NOFAIL, 0, 0, 0};
         CU(cudaMemcpy(c->wctl, &init, sizeof(init), cudaMemcpyHostToDevice));
         size_t o3 = 0;
-        TRY(ensure(&c->wbuf, &o3, (size_t)5 * WP * WP + 2 * XL_ELEMS));
+        TRY(ensure(&c->wbuf, &o3, (size_t)4 * WP * WP + 3 * XL_ELEMS));
         CU(cudaMalloc((void**)&c->wstamps, 32 * sizeof(long long)));
         CU(cudaMemset(c->wstamps, 0, 32 * sizeof(long long)));
     }
@@ -385,7 +390,8 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g2.sm_ticket = c->cvy_stagger ? c->sm_ticket : nullptr; g2.first_wave = 2 * c->sms; g2.stagger_cycles = 5200 * g2.nkq;
     g2.ctl = c->wctl; g2.gate = gate;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
-    if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
+    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_defer) K_G2D<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
+    else if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
     TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
     return 0;
@@ -511,23 +517,6 @@ static int factor_outer_panel_narrow(dhqr_context* c, cudaStream_t st, double* v
     return 0;
 }
 
-// Gram matrix of the packed panel: wsum(128 x 128) = vpk' vpk over `rows` window rows (k_gemm_vta with no trailing columns)
-static int wide_gram(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int64_t rows) {
-    const int tiles = WP / G1_BN;
-    const int nchunks = (int)((rows + KC1 - 1) / KC1);
-    const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
-    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
-    GemmVtaArgs g1;
-    g1.vpk = vpk; g1.voff = 0; g1.nv = WP; g1.A = vpk; g1.lda = 2; g1.rows = rows; g1.na = 0; g1.nchunks = nchunks;
-    g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
-    pre(c, st);
-    K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
-    TRY(post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP));
-    pre(c, st);
-    k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
-    return post(c, st, "k_wreduce");
-}
-
 // the 128-column chain (dhqr_wide.cuh): CholeskyQR2 + Householder reconstruction of a full aligned outer panel
 static bool wide_eligible(const dhqr_context* c, const Panel& p, int64_t m, int nb) {
     return c->wide_panel && nb == WP && p.kb == WP && (p.c & 31) == 0 && m - p.c >= WP;
@@ -536,44 +525,63 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
                                    int64_t col0, double* A, int64_t lda, double* alpha, int step) {
     const PanelGeom g = panel_geom(p, m);       // r0 == p.c: the window starts at the pivot row
     double* P = A + (p.c - col0) * lda + p.c;
-    double* R1 = c->wbuf, *R2 = R1 + WP * WP, *X2 = R2 + WP * WP, *Rt = X2 + WP * WP, *Y3 = Rt + WP * WP;
-    double* XL = Y3 + WP * WP, *XL3 = XL + XL_ELEMS;
+    double* R1 = c->wbuf, *R2 = R1 + WP * WP, *Rt = R2 + WP * WP, *Rr = Rt + WP * WP;
+    double* Z1 = Rr + WP * WP, *Z2 = Z1 + XL_ELEMS, *Z23 = Z2 + XL_ELEMS;
     double* vflag = vpk + KC1;                  // padding row 64 of packed column 0: travels with the V buffer
     const int nq = (int)(g.vrows / KC1);
+    long long* stamps = c->wide_trace ? c->wstamps : nullptr;
     RmulArgs r;
     r.vpk = vpk; r.ctl = c->wctl; r.step = step; r.P = nullptr; r.ldp = lda; r.mp = g.rows;
-    auto rmul = [&](int q0, int n, const double* X, double* Pout) -> int {
+    auto rmul = [&](int q0, int n, const double* Z, double* Pout) -> int {
         if (n <= 0) return 0;
-        r.q0 = q0; r.nq = n; r.XL = X; r.P = Pout;
+        r.q0 = q0; r.nq = n; r.ZL = Z; r.P = Pout;
         pre(c, st);
         k_vpk_rmul<<<std::min(n, c->sms), 256, SMEM_RMUL, st>>>(r);
         return post(c, st, "k_vpk_rmul", 2.0 * 64.0 * n * WP * 80.0);
+    };
+    // Gram matrix of the packed panel: partials of vpk' vpk over the window rows (k_gemm_vta with no trailing columns)
+    const int tiles = WP / G1_BN;
+    const int nchunks = (int)((g.rows + KC1 - 1) / KC1);
+    const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
+    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
+    auto gram = [&]() -> int {
+        GemmVtaArgs g1;
+        g1.vpk = vpk; g1.voff = 0; g1.nv = WP; g1.A = vpk; g1.lda = 2; g1.rows = g.rows; g1.na = 0; g1.nchunks = nchunks;
+        g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
+        pre(c, st);
+        K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
+        return post(c, st, "k_gram128", 2.0 * (double)g.rows * WP * WP);
     };
     pre(c, st);
     dim3 pgrid((unsigned)std::min<int64_t>((g.vrows + 255) / 256, 4 * c->sms), WP);
     k_pack<<<pgrid, 256, 0, st>>>(P, lda, g.rows, WP, 0, vpk, 0, 0, g.vrows);
     TRY(post(c, st, "k_pack"));
-    TRY(wide_gram(c, st, vpk, w, g.rows));
+    TRY(gram());
     pre(c, st);
-    long long* stamps = c->wide_trace ? c->wstamps : nullptr;
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, nullptr, XL, c->wctl, step, vflag, c->wide_kappa, stamps);
+    k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
+    TRY(post(c, st, "k_wreduce"));
+    pre(c, st);
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, Z1, c->wctl, step, vflag, c->wide_kappa, stamps);
     TRY(post(c, st, "k_chol128"));
-    TRY(rmul(0, nq, XL, nullptr));
-    TRY(wide_gram(c, st, vpk, w, g.rows));
+    TRY(rmul(0, nq, Z1, nullptr));
+    TRY(gram());
     pre(c, st);
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, X2, XL, c->wctl, step, vflag, c->wide_kappa, stamps ? stamps + 8 : nullptr);
-    TRY(post(c, st, "k_chol128"));
+    k_gram2_finish<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, w.wsum, R2, Z2, c->wctl, step, vflag);
+    TRY(post(c, st, "k_gram2_finish"));
+    pre(c, st);     // returns at once unless the first-order second pass was refused (WideCtl::need_full)
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, Z2, c->wctl, step, vflag, c->wide_kappa, stamps ? stamps + 8 : nullptr);
+    TRY(post(c, st, "k_chol128_2nd"));
     pre(c, st);
-    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(R2, R1, Rt, nullptr, c->wctl, step);
+    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(R2, R1, Rt, c->wctl, step);
     TRY(post(c, st, "k_trimm128"));
-    TRY(rmul(0, 2, XL, nullptr));
+    TRY(rmul(0, 2, Z2, nullptr));
     pre(c, st);
-    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Y3, c->wctl, step, stamps ? stamps + 16 : nullptr);
+    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Rr, c->wctl, step, stamps ? stamps + 16 : nullptr);
     TRY(post(c, st, "k_hr128"));
     pre(c, st);
-    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(X2, Y3, nullptr, XL3, c->wctl, step);
-    TRY(post(c, st, "k_trimm128"));
-    TRY(rmul(2, nq - 2, XL3, P));
+    k_trimm_z<<<10, 256, SMEM_TRIMM, st>>>(Rr, R2, Z23, c->wctl, step);
+    TRY(post(c, st, "k_trimm_z"));
+    TRY(rmul(2, nq - 2, Z23, P));
     c->wide_panels++;
     return 0;
 }
@@ -1003,6 +1011,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "cvy_defer")) {
+        c->cvy_defer = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_stagger")) {
         c->cvy_stagger = value ? 1 : 0;
     } else if (!strcmp(key, "la_trace")) {
@@ -1360,7 +1370,7 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     else if (!strcmp(which, "linv")) { src = c->ws[0].linv; have = (size_t)NBMAX * NBMAX; }
     else if (!strcmp(which, "vpk")) { src = c->vpk2[0]; have = c->vpk_elems[0]; }
     else if (!strcmp(which, "wstamps")) { src = (const double*)c->wstamps; have = c->wstamps ? 32 : 0; }
-    else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)5 * WP * WP + 2 * XL_ELEMS : 0; }
+    else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)4 * WP * WP + 3 * XL_ELEMS : 0; }
     else if (!strcmp(which, "panel_trace")) { src = (const double*)c->panel_trace; have = c->panel_trace ? (size_t)PANEL_MAXG * IB * 8 : 0; }
     else return set_err(-2, "unknown buffer '%s'", which);
     if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);

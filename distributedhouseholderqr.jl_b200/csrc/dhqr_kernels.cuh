@@ -37,6 +37,8 @@ constexpr int W_NOFAIL = 0x7fffffff;
 struct WideCtl {
     int fail_step;
     int status;      // guards of the panel in flight: 0 = fine
+    int need_full;   // second Cholesky pass: 1 = Q1'Q1 is too far from I for the first-order factor, run the full kernel
+    int pad;
 };
 __device__ __forceinline__ bool wide_gate_closed(const WideCtl* ctl, int gate) {
     return ctl && *reinterpret_cast<const volatile int*>(&ctl->fail_step) < gate;
@@ -310,7 +312,11 @@ struct GemmCvyArgs {
     int gate;
 };
 
-template <int WM, int MINB>
+// DEFER (requires nkq == MI, i.e. the 128-wide update with 32-row warp tiles): the accumulators start at zero and the C tile is
+// read in MI batches of one 8-row block each, batch i issued at the start of k-stage i and added when that stage's DMMAs are
+// done, so the loads from HBM have a whole stage to arrive instead of stalling the warps before the first DMMA
+// (profiles/r01_prof_cvy_ncu.txt: long_scoreboard 4.8 per issue, tensor pipe 79 % active with all loads up front).
+template <int WM, int MINB, bool DEFER>
 __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArgs a) {
     // WM = 2: 4 MMA warps with 64x32 warp tiles;  WM = 4: 8 MMA warps with 32x32 warp tiles (more warps per
     // scheduler to hide the C-tile loads/stores and the LDS latency)
@@ -380,29 +386,28 @@ __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArg
     const int64_t rbase = m0 + wm * WTM + (lane >> 2);
     const int cbase = n0 + wn * WTN + (lane & 3) * 2;
     double acc[MI][NJ][2];
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
+    const int fragA = (lane & 3) * LD1 + (lane >> 2);
+    const int fragB = (lane >> 2) * LDK + (lane & 3);
+    // columns [j0, j0 + NH) of the 8-row block i of this warp's C tile
+    constexpr int NH = NJ / 2;
+    auto load_half = [&](int i, int j0, double (&dst)[NH][2]) {
         const int64_t row = rbase + i * 8;
         const bool rok = row >= a.row_lo && row < a.rows;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int col = cbase + j * 8;
+        for (int j = 0; j < NH; ++j) {
+            const int col = cbase + (j0 + j) * 8;
             const double* p = a.C + (int64_t)col * a.ldc + row;
-            acc[i][j][0] = (rok && col < a.ncols) ? *p : 0.0;
-            acc[i][j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
+            dst[j][0] = (rok && col < a.ncols) ? *p : 0.0;
+            dst[j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
         }
-    }
-    const int fragA = (lane & 3) * LD1 + (lane >> 2);
-    const int fragB = (lane >> 2) * LDK + (lane & 3);
-    for (int it = 0; it < nit; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        release_prev_stage(empty, it, STAGES, lane);
-        const double* v = sV + (size_t)s * 2 * VH + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
-        const double* y = sY + (size_t)s * BN * LDK + wn * WTN * LDK + fragB;
+    };
+    const double* v0 = sV + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
+    const double* y0 = sY + wn * WTN * LDK + fragB;
+    auto mma_steps = [&](int s, int k_lo, int k_hi) {
+        const double* v = v0 + (size_t)s * 2 * VH;
+        const double* y = y0 + (size_t)s * BN * LDK;
 #pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
+        for (int kk = k_lo; kk < k_hi; ++kk) {
             double af[MI], bf[NJ];
 #pragma unroll
             for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LD1 + i * 8];
@@ -412,6 +417,58 @@ __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArg
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    };
+    if (DEFER) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < MI; ++it) {                        // nit == MI: one 8-row block of C per k-stage, in two halves
+            const int s = it % STAGES;
+            double cpre[NH][2];
+            load_half(it, 0, cpre);
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            release_prev_stage(empty, it, STAGES, lane);
+            mma_steps(s, 0, KC / 8);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)                         // predicated adds: the loop over the stages stays rolled
+                if (i == it) {
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        acc[i][j][0] += cpre[j][0];
+                        acc[i][j][1] += cpre[j][1];
+                    }
+                }
+            load_half(it, NH, cpre);
+            mma_steps(s, KC / 8, KC / 4);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+                if (i == it) {
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        acc[i][NH + j][0] += cpre[j][0];
+                        acc[i][NH + j][1] += cpre[j][1];
+                    }
+                }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            double h[NH][2];
+            load_half(i, 0, h);
+#pragma unroll
+            for (int j = 0; j < NH; ++j) { acc[i][j][0] = h[j][0]; acc[i][j][1] = h[j][1]; }
+            load_half(i, NH, h);
+#pragma unroll
+            for (int j = 0; j < NH; ++j) { acc[i][NH + j][0] = h[j][0]; acc[i][NH + j][1] = h[j][1]; }
+        }
+        for (int it = 0; it < nit; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            release_prev_stage(empty, it, STAGES, lane);
+            mma_steps(s, 0, KC / 4);
         }
     }
 #pragma unroll

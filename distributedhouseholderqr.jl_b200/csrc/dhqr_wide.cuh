@@ -6,19 +6,22 @@
 //
 //   pack      P -> vpk (packed working copy, stays the V operand of the trailing GEMMs)
 //   gram      G1 = P'P                (k_gemm_vta<128> with no trailing columns + k_wreduce)
-//   chol128   R1 = chol(G1), X1 = R1^{-1}                       one CTA
-//   rmul      vpk <- vpk X1  (= Q1)                              DMMA, one 64-row chunk per CTA iteration
-//   gram      G2 = Q1'Q1
-//   chol128   guard |G2 - I|, R2 = chol(G2), X2 = R2^{-1}
+//   chol128   R1 = chol(G1); Z1 = blocked inverse operand of R1                                one CTA
+//   rmul      vpk <- vpk R1^{-1}  (= Q1): row-local blocked triangular solve on the fp64 tensor pipe, 64-row chunks
+//   gram      G2 = Q1'Q1;  gram2_finish: guard |G2 - I|, R2 = I + U, Z2 = I - U to first order (U = striu(E) + diag(E)/2,
+//             E = G2 - I) when max|E| <= 1e-9, which is every panel that is not nearly rank deficient; else chol128 again
 //   trimm     Rt = R2 R1
-//   rmul      top two chunks <- Q1top X2 (= Wt)
-//   hr128     signed LU of Wt (Householder reconstruction), top block of the output (V, R, alpha), Y3 = Rr^{-1}
-//   trimm     X3 = X2 Y3
-//   rmul      rows below the top block: vpk <- Q1 X3 (= V), also written to the caller's matrix
+//   rmul      top two chunks <- Q1top R2^{-1} (= Wt)
+//   hr128     signed LU of Wt (Householder reconstruction), top block of the output (V, R, alpha), Rr     one CTA
+//   trimm_z   Z23 = blocked inverse operand of Rr R2
+//   rmul      rows below the top block: vpk <- Q1 (Rr R2)^{-1} (= V), also written to the caller's matrix
 //
-// The guards (positive finite Cholesky pivots, ||Q1'Q1 - I|| <= 1/4) are evaluated on the device; a refused panel records its
-// index in WideCtl::fail_step, every later kernel that would write the caller's matrix returns at once, and the driver redoes
-// the factorisation from that panel with the 32-column chain (dhqr_api.cu: qr_blocked).
+// "Blocked inverse operand" Z of an upper triangular R (32-column blocks): Z_bb = inv(R_bb), Z_ab = -R_ab inv(R_bb) (a < b), so
+// that X = P R^{-1} is X_b = P_b Z_bb + sum_{a<b} X_a Z_ab: GEMM-shaped, row local, and only 32 x 32 blocks are inverted.
+//
+// The guards (positive finite Cholesky pivots, a conditioning estimate of R1, ||Q1'Q1 - I|| <= 1/4) are evaluated on the device;
+// a refused panel records its index in WideCtl::fail_step, every later kernel that would write the caller's matrix returns at
+// once, and the driver redoes the factorisation from that panel with the 32-column chain (dhqr_api.cu: qr_blocked).
 #pragma once
 #include "dhqr_kernels.cuh"
 
@@ -54,99 +57,53 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// In-place inverse of the upper triangle of A (row-major, leading dimension WLD, 128 x 128) by recursive doubling:
-// 8 x 8 diagonal blocks by back substitution (dinv = 1 / diag), then X12 = -X11 (R12 X22) for block sizes 8 .. 64.
-// The strict lower triangle is neither read nor written.  T: scratch of 4096 doubles.  All threads of the CTA call it.
-// (Four partial sums per dot product: the loops are latency bound, one warp instruction in flight per sum.)
+// Inverse of an upper triangular 32 x 32 block by ONE warp (lane = column of the inverse, back substitution in registers;
+// every lane runs the same 496 multiply-adds, the entries of R are broadcast loads).  R: row-major, leading dimension ldr;
+// dinv = 1 / diag(R) or null; D: row-major 32 x 32 with leading dimension LDD (zeros below the diagonal).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void triu_inv128(double* A, const double* dinv, double* T, int tid, int nthreads) {
-    if (tid < WP) {
-        const int d = tid >> 3, c = tid & 7;
-        const double* Rb = A + (d * 8) * WLD + d * 8;
-        double x[8];
+constexpr int LDD = 33;   // leading dimension of an inverted 32 x 32 block in shared memory
+__device__ __forceinline__ void triu_inv32_warp(const double* R, int ldr, const double* dinv, double* D, int lane) {
+    double x[32];
 #pragma unroll
-        for (int i = 7; i >= 0; --i) {
-            double s = i == c ? 1.0 : 0.0;
+    for (int i = 31; i >= 0; --i) {
+        double s = i == lane ? 1.0 : 0.0;
 #pragma unroll
-            for (int p = i + 1; p < 8; ++p)
-                if (p <= c) s -= Rb[i * WLD + p] * x[p];
-            x[i] = i <= c ? s * dinv[d * 8 + i] : 0.0;
-        }
+        for (int p = i + 1; p < 32; ++p) s -= R[i * ldr + p] * x[p];       // x[p] == 0 for p > lane
+        const double di = dinv ? dinv[i] : 1.0 / R[i * ldr + i];
+        x[i] = i <= lane ? s * di : 0.0;
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) T[d * 64 + i * 8 + c] = x[i];
-    }
-    __syncthreads();
-    for (int e = tid; e < 16 * 64; e += nthreads) {
-        const int d = e >> 6, i = (e >> 3) & 7, c = e & 7;
-        if (i <= c) A[(d * 8 + i) * WLD + d * 8 + c] = T[e];
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int lb = 3; lb < 7; ++lb) {
-        const int bs = 1 << lb, per = bs * bs, tot = (WP / (2 * bs)) * per;
-        // tmp = R12 X22 : lanes run over the row i (the trip count depends on the column j only)
-        for (int e = tid; e < tot; e += nthreads) {
-            const int pi = e >> (2 * lb), r = e & (per - 1), i = r & (bs - 1), j = r >> lb, o = pi * 2 * bs;
-            const double* r12 = A + (o + i) * WLD + o + bs;
-            const double* x22 = A + (o + bs) * WLD + o + bs + j;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int p = 0;
-            for (; p + 3 <= j; p += 4) {
-                s0 += r12[p] * x22[p * WLD];
-                s1 += r12[p + 1] * x22[(p + 1) * WLD];
-                s2 += r12[p + 2] * x22[(p + 2) * WLD];
-                s3 += r12[p + 3] * x22[(p + 3) * WLD];
-            }
-            for (; p <= j; ++p) s0 += r12[p] * x22[p * WLD];
-            T[pi * per + i * bs + j] = (s0 + s1) + (s2 + s3);
-        }
-        __syncthreads();
-        // X12 = -X11 tmp : lanes run over the column j (the trip count depends on the row i only)
-        for (int e = tid; e < tot; e += nthreads) {
-            const int pi = e >> (2 * lb), r = e & (per - 1), j = r & (bs - 1), i = r >> lb, o = pi * 2 * bs;
-            const double* x11 = A + (o + i) * WLD + o;
-            const double* tm = T + pi * per + j;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int p = i;
-            for (; p + 3 < bs; p += 4) {
-                s0 += x11[p] * tm[p * bs];
-                s1 += x11[p + 1] * tm[(p + 1) * bs];
-                s2 += x11[p + 2] * tm[(p + 2) * bs];
-                s3 += x11[p + 3] * tm[(p + 3) * bs];
-            }
-            for (; p < bs; ++p) s0 += x11[p] * tm[p * bs];
-            A[(o + i) * WLD + o + bs + j] = -((s0 + s1) + (s2 + s3));
-        }
-        __syncthreads();
-    }
+    for (int i = 0; i < 32; ++i) D[i * LDD + lane] = x[i];
 }
 
 // ------------------------------------------------------------------------------------------------
-// chol128: R = chol(G) (upper), X = R^{-1}; one CTA of 512 threads.  G: [j * 128 + i] as k_wreduce leaves it.
-//   second == 0: guards = positive finite pivots and ||D X||_F <= kappa_max, D = diag(||p_j||) (the explicit inverse costs
-//                ~1e-17 x that number in ||QR - A|| / ||A||, scale invariant: tests/test_widepanel_model.py)
-//   second != 0: guard max |G - I| <= 1 / (4 * 128) first (the first pass left Q1 close enough to orthonormal for the second
-//                pass to finish the job; refuses NaN / Inf as well).
+// chol128: R = chol(G) (upper) and its blocked inverse operand Z; one CTA of 512 threads.  G: [j * 128 + i] (k_wreduce).
+//   second == 0: guards = positive finite pivots and the conditioning estimate
+//                    est^2 = sum_b ||diag(||p_j||) Z_bb||_F^2 + sum_{a<b} ||Z_ab||_F^2 <= kappa_max^2
+//                (inverting diagonal blocks explicitly costs ~1e-17 x est in ||QR - A|| / ||A||, invariant under column
+//                scaling: tests/test_widepanel_model.py)
+//   second != 0: the fallback of k_gram2_finish (runs only when WideCtl::need_full is set): guard max |G - I| <= 1/(4*128).
 //   The trailing matrix lives in registers: thread (warp w, lane l) holds rows w + 16 a, columns l + 32 b.  Step j: the warp
 //   that owns row j scales it (one rsqrt) and publishes it through shared memory, one barrier, and every thread updates its
-//   8 x 4 block (the symmetric update needs row j only).  The published rows are R; X by recursive doubling afterwards.
-//   Outputs: Rp, Xp plain column-major upper triangular (zeros below), XL the rmul operand layout of X.
+//   8 x 4 block (the symmetric update needs row j only).  The published rows are R.
 // ------------------------------------------------------------------------------------------------
-constexpr size_t SMEM_WIDE1 = ((size_t)WP * WLD + 4096 + 8 * WP) * 8 + 64;
+constexpr int WT = 4 * 32 * LDD;   // scratch: four inverted diagonal blocks
+constexpr size_t SMEM_WIDE1 = ((size_t)WP * WLD + WT + 8 * WP) * 8 + 64;
 
 __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G, int second, double* __restrict__ Rp,
-                                                    double* __restrict__ Xp, double* __restrict__ XL, WideCtl* ctl, int step,
-                                                    double* vflag, double kappa_max, long long* stamps) {
+                                                    double* __restrict__ ZL, WideCtl* ctl, int step, double* vflag,
+                                                    double kappa_max, long long* stamps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* A = reinterpret_cast<double*>(smem_raw);   // [128][WLD] row-major: R, then X
-    double* T = A + WP * WLD;                            // 4096
-    double* rinv = T + 4096;                             // 128
+    double* A = reinterpret_cast<double*>(smem_raw);   // [128][WLD] row-major: R
+    double* T = A + WP * WLD;                            // WT: the four inverted diagonal blocks
+    double* rinv = T + WT;                               // 128
     double* dn = rinv + WP;                              // 128: ||p_j|| = sqrt(G_jj)
     double* rowbuf = dn + WP;                            // [2][128]
     double* red = rowbuf + 2 * WP;                       // 16 (+ spare)
     int* sbad = reinterpret_cast<int*>(rinv + 8 * WP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (wide_gate_closed(ctl, step) || ctl->status) return;
+    if (second && !ctl->need_full) return;
     const long long t0 = clock64();
     if (tid == 0) *sbad = 0;
     double g[8][4];
@@ -214,18 +171,34 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
             const int i = e & (WP - 1), j = e >> 7;
             Rp[e] = i <= j ? A[i * WLD + j] : 0.0;
         }
+        if (warp < 4) triu_inv32_warp(A + (32 * warp) * WLD + 32 * warp, WLD, rinv + 32 * warp, T + warp * 32 * LDD, lane);
         __syncthreads();
-        triu_inv128(A, rinv, T, tid, 512);
         if (stamps && tid == 0) stamps[2] = clock64() - t0;
-        if (!second) {                                   // ||D X||_F
-            double acc = 0.0;
-            for (int e = tid; e < WP * WP; e += 512) {
-                const int k = e >> 7, n = e & (WP - 1);
-                if (k <= n) {
-                    const double v = dn[k] * A[k * WLD + n];
-                    acc += v * v;
-                }
+        double acc = 0.0;
+        for (int e = tid; e < 4096; e += 512) {          // Z_bb = inv(R_bb)
+            const int b = e >> 10, c = (e >> 5) & 31, i = e & 31;
+            const double v = T[b * 32 * LDD + i * LDD + c];
+            ZL[xl_off(b) + c * xl_ld(b) + 32 * b + i] = v;
+            const double sv = dn[32 * b + i] * v;
+            acc += sv * sv;
+        }
+        for (int e = tid; e < 6144; e += 512) {          // Z_ab = -R_ab inv(R_bb), a < b
+            const int pr = e >> 10, c = (e >> 5) & 31, i = e & 31;
+            const int a = pr < 3 ? 0 : (pr < 5 ? 1 : 2), b = pr < 3 ? pr + 1 : (pr < 5 ? pr - 1 : 3);
+            const double* r = A + (32 * a + i) * WLD + 32 * b;
+            const double* d = T + b * 32 * LDD + c;
+            double s0 = 0.0, s1 = 0.0;
+            int p = 0;
+            for (; p + 1 <= c; p += 2) {
+                s0 += r[p] * d[p * LDD];
+                s1 += r[p + 1] * d[(p + 1) * LDD];
             }
+            if (p <= c) s0 += r[p] * d[p * LDD];
+            const double v = -(s0 + s1);
+            ZL[xl_off(b) + c * xl_ld(b) + 32 * a + i] = v;
+            acc += v * v;
+        }
+        if (!second) {
             acc = warp_sum(acc);
             if (lane == 0) red[warp] = acc;
             __syncthreads();
@@ -237,46 +210,73 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
             __syncthreads();
         }
     }
-    if (*sbad) {
-        if (tid == 0) {
-            ctl->status = 1;
-            atomicMin(&ctl->fail_step, step);
-            if (vflag) *vflag = 1.0;
-        }
-        return;
-    }
-    if (Xp)
-        for (int e = tid; e < WP * WP; e += 512) {
-            const int i = e & (WP - 1), j = e >> 7;
-            Xp[e] = i <= j ? A[i * WLD + j] : 0.0;
-        }
-#pragma unroll
-    for (int nbk = 0; nbk < 4; ++nbk) {
-        const int ld = xl_ld(nbk), kk = 32 * (nbk + 1);
-        for (int e = tid; e < 32 * kk; e += 512) {
-            const int k = e % kk, nin = e / kk, n = 32 * nbk + nin;
-            XL[xl_off(nbk) + nin * ld + k] = k <= n ? A[k * WLD + n] : 0.0;
-        }
+    if (*sbad && tid == 0) {
+        ctl->status = 1;
+        atomicMin(&ctl->fail_step, step);
+        if (vflag) *vflag = 1.0;
     }
     if (stamps && tid == 0) stamps[3] = clock64() - t0;
 }
 
 // ------------------------------------------------------------------------------------------------
+// gram2_finish: the split-K reduction of the second Gram matrix (as k_wreduce, fixed order) fused with the second Cholesky
+// pass in its first-order form.  E = G2 - I is the loss of orthogonality of the first pass; with U = striu(E) + diag(E)/2,
+// chol(I + E) = I + U + O(E^2) and its inverse is I - U + O(E^2).  max|E| <= 1e-9 bounds the neglected terms by
+// 128 * 1e-18, far below rounding; larger E sets WideCtl::need_full and k_chol128(second) redoes the pass.
+// One element per thread (grid 64 x 256).  Outputs: Ws (G2), Rp = R2 plain, ZL = its blocked inverse operand.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram2_finish(const double* __restrict__ Wp, int64_t pstride, int nsplit, double* __restrict__ Ws,
+                                                      double* __restrict__ Rp, double* __restrict__ ZL, WideCtl* ctl, int step,
+                                                      double* vflag) {
+    if (wide_gate_closed(ctl, step) || ctl->status) return;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= WP * WP) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 4 <= nsplit; p += 4) {
+        s0 += Wp[(int64_t)p * pstride + e];
+        s1 += Wp[(int64_t)(p + 1) * pstride + e];
+        s2 += Wp[(int64_t)(p + 2) * pstride + e];
+        s3 += Wp[(int64_t)(p + 3) * pstride + e];
+    }
+    for (; p < nsplit; ++p) s0 += Wp[(int64_t)p * pstride + e];
+    const double g = (s0 + s1) + (s2 + s3);
+    Ws[e] = g;
+    const int i = e & (WP - 1), j = e >> 7;              // row, column
+    const double E = g - (i == j ? 1.0 : 0.0);
+    if (!(fabs(E) <= 0.25 / WP)) {
+        ctl->status = 1;
+        atomicMin(&ctl->fail_step, step);
+        if (vflag) *vflag = 1.0;
+    }
+    if (!(fabs(E) <= 1e-9)) ctl->need_full = 1;
+    const double u = i == j ? 0.5 * E : E;
+    Rp[e] = i < j ? u : (i == j ? 1.0 + u : 0.0);
+    const int nbk = j >> 5;
+    if (i < 32 * (nbk + 1)) ZL[xl_off(nbk) + (j & 31) * xl_ld(nbk) + i] = i < j ? -u : (i == j ? 1.0 - u : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // trimm128: C = A B for upper-triangular 128 x 128 operands (plain column-major, zeros below the diagonal);
 // grid = the 10 upper 32 x 32 blocks; every block loads all its operand blocks in one go (one global round trip).
-// Outputs: Cp plain and / or CL in the rmul operand layout (either may be null).
 // ------------------------------------------------------------------------------------------------
-constexpr size_t SMEM_TRIMM = (size_t)8 * 32 * 33 * 8;
+constexpr size_t SMEM_TRIMM = (size_t)11 * 32 * 33 * 8;
+
+__device__ __forceinline__ void trimm_block_id(int bid, int& ib, int& jb) {
+    ib = 0;
+    int r = bid;
+    while (r >= 4 - ib) { r -= 4 - ib; ++ib; }
+    jb = ib + r;
+}
 
 __global__ void __launch_bounds__(256) k_trimm128(const double* __restrict__ Am, const double* __restrict__ Bm,
-                                                  double* __restrict__ Cp, double* __restrict__ CL, const WideCtl* ctl, int step) {
+                                                  double* __restrict__ Cp, const WideCtl* ctl, int step) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);   // [4][32][33]
     double* sB = sA + 4 * 32 * 33;
     if (wide_gate_closed(ctl, step) || ctl->status) return;
-    int ib = 0, r = blockIdx.x;
-    while (r >= 4 - ib) { r -= 4 - ib; ++ib; }
-    const int jb = ib + r;
+    int ib, jb;
+    trimm_block_id(blockIdx.x, ib, jb);
     const int tid = threadIdx.x, i = tid & 31, jq = tid >> 5;   // thread: row i, columns jq, jq + 8, jq + 16, jq + 24
     for (int pb = ib; pb <= jb; ++pb)
 #pragma unroll
@@ -298,30 +298,97 @@ __global__ void __launch_bounds__(256) k_trimm128(const double* __restrict__ Am,
         }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int row = ib * 32 + i, cin = jq + 8 * q, col = jb * 32 + cin;
-        if (Cp) Cp[(size_t)col * WP + row] = acc[q];
-        if (CL) CL[xl_off(jb) + cin * xl_ld(jb) + row] = acc[q];
-    }
+    for (int q = 0; q < 4; ++q) Cp[(size_t)(jb * 32 + jq + 8 * q) * WP + ib * 32 + i] = acc[q];
     // the blocks below the diagonal are zero in the plain layout; whoever owns the diagonal block of a block column clears them
-    if (Cp && ib == jb)
+    if (ib == jb)
         for (int pb = jb + 1; pb < 4; ++pb)
 #pragma unroll
             for (int q = 0; q < 4; ++q) Cp[(size_t)(jb * 32 + jq + 8 * q) * WP + pb * 32 + i] = 0.0;
 }
 
+// trimm_z: Z = blocked inverse operand of C = A B (A, B upper triangular, plain), without forming C in memory: block (a, b)
+// of the grid computes C_ab and C_bb, inverts C_bb with one warp, and writes Z_bb = inv(C_bb) (a == b) or Z_ab = -C_ab inv(C_bb).
+__global__ void __launch_bounds__(256) k_trimm_z(const double* __restrict__ Am, const double* __restrict__ Bm, double* __restrict__ ZL,
+                                                 const WideCtl* ctl, int step) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);   // [4][32][33]: A(a, a..b)
+    double* sB = sA + 4 * 32 * 33;                       // [4][32][33]: B(a..b, b)
+    double* sA2 = sB + 4 * 32 * 33;                      // A(b, b)
+    double* sC = sA2 + 32 * 33;                          // C_ab, then C_bb
+    double* sD = sC + 32 * 33;                           // inv(C_bb), [32][LDD]
+    if (wide_gate_closed(ctl, step) || ctl->status) return;
+    int ib, jb;
+    trimm_block_id(blockIdx.x, ib, jb);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = lane, jq = warp;
+    for (int pb = ib; pb <= jb; ++pb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = jq + 8 * q;
+            sA[((pb - ib) * 32 + i) * 33 + c] = Am[(size_t)(pb * 32 + c) * WP + ib * 32 + i];
+            sB[((pb - ib) * 32 + i) * 33 + c] = Bm[(size_t)(jb * 32 + c) * WP + pb * 32 + i];
+        }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sA2[i * 33 + jq + 8 * q] = Am[(size_t)(jb * 32 + jq + 8 * q) * WP + jb * 32 + i];
+    __syncthreads();
+    double cab[4] = {0.0, 0.0, 0.0, 0.0}, cbb[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int pb = 0; pb <= jb - ib; ++pb) {
+        const double* a = sA + (pb * 32 + i) * 33;
+        const double* bq = sB + pb * 32 * 33 + jq;
+#pragma unroll 8
+        for (int p = 0; p < 32; ++p) {
+            const double av = a[p];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cab[q] += av * bq[p * 33 + 8 * q];
+        }
+    }
+    {
+        const double* a = sA2 + i * 33;
+        const double* bq = sB + (jb - ib) * 32 * 33 + jq;
+#pragma unroll 8
+        for (int p = 0; p < 32; ++p) {
+            const double av = a[p];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cbb[q] += av * bq[p * 33 + 8 * q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sC[i * 33 + jq + 8 * q] = cbb[q];
+    __syncthreads();
+    if (warp == 0) triu_inv32_warp(sC, 33, nullptr, sD, lane);
+    __syncthreads();
+    if (ib == jb) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = jq + 8 * q;
+            ZL[xl_off(jb) + c * xl_ld(jb) + 32 * jb + i] = sD[i * LDD + c];
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sC[i * 33 + jq + 8 * q] = cab[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = jq + 8 * q;
+        double s = 0.0;
+        for (int p = 0; p <= c; ++p) s += sC[i * 33 + p] * sD[p * LDD + c];
+        ZL[xl_off(jb) + c * xl_ld(jb) + 32 * ib + i] = -s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// vpk_rmul:  chunks [q0, q0 + nq) of vpk  <-  chunk * X   (X upper triangular 128 x 128 in the XL layout), on the fp64
-// tensor pipe; optionally the result also goes to the caller's matrix (rows < mp of the panel at P).
-//   A CTA keeps X in shared memory and walks over its chunks with two chunk buffers: the bulk copy of the next chunk and the
-//   bulk store of the previous result overlap the DMMAs of the current one.  8 warps x (16 rows x two 32-column blocks paired
-//   (0,3) / (1,2) so that every warp runs the same number of k steps of the triangular product); the result overwrites the
-//   chunk in shared memory and goes back with one bulk store.
+// vpk_rmul:  chunks [q0, q0 + nq) of vpk  <-  chunk * R^{-1} through the blocked inverse operand Z of R (ZL layout), on the
+// fp64 tensor pipe; optionally the result also goes to the caller's matrix (rows < mp of the panel at P).
+//   The solve is row local: warp w owns rows 8w .. 8w+7 of the 64-row chunk and runs the four 32-column block steps
+//   X_b = P_b Z_bb + sum_{a<b} X_a Z_ab by itself (the finished blocks overwrite the chunk in shared memory and are the A
+//   operand of the later steps: __syncwarp only).  A CTA keeps Z in shared memory and walks over its chunks with two chunk
+//   buffers: the bulk copy of the next chunk and the bulk store of the previous result overlap the DMMAs of the current one.
 // ------------------------------------------------------------------------------------------------
 struct RmulArgs {
     double* vpk;
     int q0, nq;
-    const double* XL;
+    const double* ZL;
     double* P;          // null: packed output only
     int64_t ldp, mp;
     const WideCtl* ctl;
@@ -348,13 +415,12 @@ __global__ void __launch_bounds__(256, 1) k_vpk_rmul(RmulArgs a) {
         const uint32_t cb = VPK_CHUNK * 8;
         mbar_arrive_expect_tx(&bar[buf], cb + (withX ? XL_ELEMS * 8 : 0));
         if (withX)
-            for (int o = 0; o < XL_ELEMS; o += 3584) bulk_g2s(sX + o, a.XL + o, 3584 * 8, &bar[buf]);
+            for (int o = 0; o < XL_ELEMS; o += 3584) bulk_g2s(sX + o, a.ZL + o, 3584 * 8, &bar[buf]);
         const double* src = a.vpk + (int64_t)qq * VPK_CHUNK;
         double* dst = sC0 + buf * VPK_CHUNK;
         for (int o = 0; o < VPK_CHUNK; o += VPK_CHUNK / 4) bulk_g2s(dst + o, src + o, VPK_CHUNK * 2, &bar[buf]);
     };
     if (q < qend && tid == 0) load(q, 0, true);
-    const int rb = warp & 3, pr = warp >> 2;
     for (int it = 0; q < qend; q += qstep, ++it) {
         const int buf = it & 1;
         double* sC = sC0 + buf * VPK_CHUNK;
@@ -363,44 +429,31 @@ __global__ void __launch_bounds__(256, 1) k_vpk_rmul(RmulArgs a) {
             load(q + qstep, buf ^ 1, false);
         }
         mbar_wait(&bar[buf], (it >> 1) & 1);
-        double acc[2][2][4][2];
+        const double* pa = sC + (lane & 3) * LD1 + 8 * warp + (lane >> 2);
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 4; ++b) {
+            const int ld = xl_ld(b), k4 = 8 * (b + 1);
+            const double* pb = sX + xl_off(b) + (lane >> 2) * ld + (lane & 3);
+            double acc[4][2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[b][i][j][0] = acc[b][i][j][1] = 0.0;
-        const double* pa = sC + (lane & 3) * LD1 + 16 * rb + (lane >> 2);
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int nbk = b == 0 ? pr : 3 - pr;
-            const int ld = xl_ld(nbk), k4 = 8 * (nbk + 1);
-            const double* pb = sX + xl_off(nbk) + (lane >> 2) * ld + (lane & 3);
+            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
 #pragma unroll 4
             for (int kk = 0; kk < k4; ++kk) {
-                const double a0 = pa[kk * 4 * LD1], a1 = pa[kk * 4 * LD1 + 8];
+                const double a0 = pa[kk * 4 * LD1];
                 double bf[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * ld + kk * 4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dmma(acc[b][0][j][0], acc[b][0][j][1], a0, bf[j]);
-                    dmma(acc[b][1][j][0], acc[b][1][j][1], a1, bf[j]);
-                }
+                for (int j = 0; j < 4; ++j) dmma(acc[j][0], acc[j][1], a0, bf[j]);
             }
-        }
-        __syncthreads();                                      // every warp has read its A fragments
+            __syncwarp();                                     // every lane has read P_b of the warp's rows
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int nbk = b == 0 ? pr : 3 - pr;
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int row = 16 * rb + 8 * i + (lane >> 2), col = 32 * nbk + 8 * j + 2 * (lane & 3);
-                    sC[col * LD1 + row] = acc[b][i][j][0];
-                    sC[(col + 1) * LD1 + row] = acc[b][i][j][1];
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int row = 8 * warp + (lane >> 2), col = 32 * b + 8 * j + 2 * (lane & 3);
+                sC[col * LD1 + row] = acc[j][0];
+                sC[(col + 1) * LD1 + row] = acc[j][1];
+            }
+            __syncwarp();                                     // X_b is the A operand of the next block steps
         }
         fence_proxy_async();
         __syncthreads();
@@ -427,18 +480,17 @@ __global__ void __launch_bounds__(256, 1) k_vpk_rmul(RmulArgs a) {
 //   Wt = first 128 rows of vpk (= rows of the orthonormal factor Q2).  Signed LU, row j frozen at step j:
 //   S_j = -sign(w_jj), U_jj = 1 + |w_jj|, W(i,k) += (S_j / U_jj) W(i,j) W(j,k).  In the reference's storage (S:127-135):
 //   v_ij = W_ij^(j) / sqrt(U_jj) (i > j), v_jj = -S_j sqrt(U_jj), alpha_j = S_j Rt_jj, R_ij = S_i Rt_ij (i < j).
-//   The rows below the top block are V = Q Rr^{-1}, Rr = diag(sqrt(U)) (I + diag(-S/U) striu(W)); this kernel leaves
-//   Y3 = Rr^{-1} (plain) for k_trimm128 / k_vpk_rmul.
+//   The rows below the top block are V = Q Rr^{-1}, Rr = diag(sqrt(U)) (I + diag(-S/U) striu(W)), left in Rrp (plain).
 //   Like k_chol128 the matrix lives in registers (rows w + 16 a, columns l + 32 b per thread); a step publishes column j and
 //   row j through double-buffered shared memory: one barrier per step.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, const double* __restrict__ Rt, double* __restrict__ P,
-                                                  int64_t ldp, double* __restrict__ alpha, double* __restrict__ Y3,
+                                                  int64_t ldp, double* __restrict__ alpha, double* __restrict__ Rrp,
                                                   const WideCtl* ctl, int step, long long* stamps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Wt = reinterpret_cast<double*>(smem_raw);   // [128][WLD] row-major
     double* T = Wt + WP * WLD;
-    double* Sg = T + 4096;
+    double* Sg = T + WT;
     double* Ud = Sg + WP;
     double* rsq = Ud + WP;
     double* colbuf = rsq + WP;                           // [2][128]
@@ -502,27 +554,15 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
     if (stamps && tid == 0) stamps[5] = clock64() - t0;
     for (int e = tid; e < WP * WP; e += 512) {
         const int i = e & (WP - 1), j = e >> 7;
-        double v;
-        if (i > j) v = Wt[i * WLD + j] * rsq[j];
-        else if (i == j) v = -Sg[j] * (Ud[j] * rsq[j]);
-        else v = Sg[i] * Rt[e];
+        const double wij = Wt[i * WLD + j];
+        double v, rr;
+        if (i > j) { v = wij * rsq[j]; rr = 0.0; }
+        else if (i == j) { v = -Sg[j] * (Ud[j] * rsq[j]); rr = Ud[i] * rsq[i]; }
+        else { v = Sg[i] * Rt[e]; rr = (-Sg[i] / Ud[i]) * wij * (Ud[i] * rsq[i]); }
         P[(int64_t)j * ldp + i] = v;
         vpk[vpk_index(i, j)] = i >= j ? v : 0.0;
+        Rrp[e] = rr;
         if (i == j) alpha[j] = Sg[j] * Rt[e];
-    }
-    __syncthreads();
-    for (int e = tid; e < WP * WP; e += 512) {           // Rr over the upper triangle, in place
-        const int i = e >> 7, k = e & (WP - 1);
-        if (k >= i) {
-            const double sq = Ud[i] * rsq[i];
-            Wt[i * WLD + k] = k == i ? sq : (-Sg[i] / Ud[i]) * Wt[i * WLD + k] * sq;
-        }
-    }
-    __syncthreads();
-    triu_inv128(Wt, rsq, T, tid, 512);
-    for (int e = tid; e < WP * WP; e += 512) {
-        const int i = e & (WP - 1), j = e >> 7;
-        Y3[e] = i <= j ? Wt[i * WLD + j] : 0.0;
     }
     if (stamps && tid == 0) stamps[6] = clock64() - t0;
 }
@@ -531,6 +571,7 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
 __global__ void k_wide_begin(WideCtl* ctl, double* vflag) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->status = 0;
+        ctl->need_full = 0;
         *vflag = 0.0;
     }
 }
@@ -538,6 +579,7 @@ __global__ void k_wide_reset(WideCtl* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->fail_step = W_NOFAIL;
         ctl->status = 0;
+        ctl->need_full = 0;
     }
 }
 // after a V buffer arrived from another rank: take over the owner's verdict on the panel

@@ -99,9 +99,27 @@ def test_degenerate_panels_are_refused():
             assert not W.wide_panel(Q)[2]
 
 
-def test_explicit_inverse_by_doubling():
+def test_inverse_operand_solves_from_the_right():
     rng = np.random.default_rng(1)
     R = np.triu(rng.standard_normal((128, 128))) + 12 * np.eye(128)
     X = W.triu_inverse(R)
-    assert np.abs(X @ R - np.eye(128)).max() < 1e-14
-    assert np.abs(np.tril(X, -1)).max() == 0.0
+    assert np.abs(X @ R - np.eye(128)).max() < 1e-14 and np.abs(np.tril(X, -1)).max() == 0.0
+    P = rng.standard_normal((300, 128))
+    Y = W.solve_right(P, W.inverse_operand(R))
+    assert np.abs(Y @ R - P).max() < 1e-13 * np.abs(P).max() * 128
+
+
+def test_second_pass_first_order_factor():
+    # chol(I + E) = I + U + O(E^2), inverse I - U + O(E^2) with U = striu(E) + diag(E)/2: exact to rounding below 1e-9
+    rng = np.random.default_rng(2)
+    for mag in (1e-15, 1e-12, 1e-9 / 2):
+        E = rng.uniform(-mag, mag, (128, 128))
+        E = (E + E.T) / 2
+        R2, Z2, ok, fo = W.second_pass(np.eye(128) + E)
+        assert ok and fo
+        Rc, _ = W.cholesky_upper(np.eye(128) + E)
+        assert np.abs(R2 - Rc).max() < 128 * mag * mag + 4e-16
+        assert np.abs(Z2 @ R2 - np.eye(128)).max() < 128 * mag * mag + 4e-16
+    R2, Z2, ok, fo = W.second_pass(np.eye(128) + 1e-6 * np.ones((128, 128)))
+    assert ok and not fo
+    assert not W.second_pass(np.eye(128) + 1e-2 * np.ones((128, 128)))[2]

@@ -1,12 +1,16 @@
-"""numpy restatement of the 128-column panel chain (k_chol128 / k_vpk_rmul / k_hr128 / k_trimm128 in
-distributedhouseholderqr.jl_b200/csrc/dhqr_kernels.cuh), stage by stage:
+"""numpy restatement of the 128-column panel chain (k_chol128 / k_gram2_finish / k_vpk_rmul / k_hr128 / k_trimm128 / k_trimm_z in
+distributedhouseholderqr.jl_b200/csrc/dhqr_wide.cuh), stage by stage:
 
-    G1 = P'P          R1 = chol(G1)     X1 = R1^{-1} (explicit, recursive doubling)      Q1 = P X1
-    G2 = Q1'Q1        R2 = chol(G2)     X2 = R2^{-1}                                      (orthogonality guard on G2)
-    Wt = Q1[:nb] X2   signed LU of Wt (Householder reconstruction: Ballard, Demmel, Grigori, Jacquelin, Nguyen, Solomonik 2014)
-    Rr = diag(sqrt(Ud)) (I + diag(cl) striu(U))      X3 = X2 Rr^{-1}      V[nb:] = Q1[nb:] X3      Rt = R2 R1
+    G1 = P'P          R1 = chol(G1)     Z1 = blocked inverse operand of R1                Q1 = P R1^{-1} (through Z1)
+    G2 = Q1'Q1        E = G2 - I        R2 = I + U, Z2 = I - U with U = striu(E) + diag(E)/2 when max|E| <= 1e-9
+                                        (first order in E; otherwise R2 = chol(G2) like the first pass)
+    Wt = Q1[:nb] R2^{-1}   signed LU of Wt (Householder reconstruction: Ballard, Demmel, Grigori, Jacquelin, Nguyen, Solomonik 2014)
+    Rr = diag(sqrt(Ud)) (I + diag(cl) striu(U))      V[nb:] = Q1[nb:] (Rr R2)^{-1}      Rt = R2 R1
 
-producing the reference's storage (S:127-135: v scaled to |v|^2 = 2 in the lower trapezoid including the diagonal, R above,
+"Blocked inverse operand" Z of an upper triangular R, 32-column blocks: Z_bb = inv(R_bb), Z_ab = -R_ab inv(R_bb) for a < b, so
+that X = P R^{-1} is the GEMM-shaped, row-local recurrence X_b = P_b Z_bb + sum_{a<b} X_a Z_ab.
+
+The output is the reference's storage (S:127-135: v scaled to |v|^2 = 2 in the lower trapezoid including the diagonal, R above,
 diag(R) in alpha) for a whole outer panel with three grid-wide reductions instead of one per column.
 
 Test infrastructure only (tests/test_widepanel_model.py): pins on the CPU that this algorithm yields the reflectors of the
@@ -64,10 +68,45 @@ def triu_inverse(R, base=8):
     return X
 
 
-def kappa_estimate(R, X):
-    """||D X||_F with D = diag(column norms of R) = diag(||p_j||): invariant under column scaling of the panel."""
+BS = 32                  # block size of the inverse operand
+FIRST_ORDER_MAX = 1.0e-9 # second pass: max|Q1'Q1 - I| up to which chol(I + E) is taken to first order in E
+
+
+def inverse_operand(R):
+    """Z_bb = inv(R_bb), Z_ab = -R_ab inv(R_bb) (a < b)."""
+    n = R.shape[0]
+    Z = np.zeros((n, n))
+    for b in range(0, n, BS):
+        D = triu_inverse(R[b:b + BS, b:b + BS], base=BS)
+        Z[b:b + BS, b:b + BS] = D
+        for a in range(0, b, BS):
+            Z[a:a + BS, b:b + BS] = -(R[a:a + BS, b:b + BS] @ D)
+    return Z
+
+
+def solve_right(P, Z):
+    """X = P R^{-1} through the inverse operand Z of R (k_vpk_rmul): X_b = P_b Z_bb + sum_{a<b} X_a Z_ab."""
+    X = np.array(P, dtype=np.float64, copy=True)
+    n = Z.shape[0]
+    for b in range(0, n, BS):
+        acc = P[:, b:b + BS] @ Z[b:b + BS, b:b + BS]
+        for a in range(0, b, BS):
+            acc = acc + X[:, a:a + BS] @ Z[a:a + BS, b:b + BS]
+        X[:, b:b + BS] = acc
+    return X
+
+
+def kappa_estimate(R, Z):
+    """sqrt(sum_b ||D_b Z_bb||_F^2 + sum_{a<b} ||Z_ab||_F^2), D = diag(column norms of R) = diag(||p_j||): invariant under
+    column scaling of the panel; ~ the condition number of the column-normalised panel."""
     d = np.sqrt((R * R).sum(0))
-    return float(np.sqrt(((d[:, None] * X) ** 2).sum()))
+    n = R.shape[0]
+    s = 0.0
+    for b in range(0, n, BS):
+        s += ((d[b:b + BS, None] * Z[b:b + BS, b:b + BS]) ** 2).sum()
+        for a in range(0, b, BS):
+            s += (Z[a:a + BS, b:b + BS] ** 2).sum()
+    return float(np.sqrt(s))
 
 
 def signed_lu(W):
@@ -85,36 +124,45 @@ def signed_lu(W):
     return Wt, Sg, Ud
 
 
+def second_pass(G2):
+    """(R2, Z2, ok, first_order) from G2 = Q1'Q1: guard, then the first-order factor or a full Cholesky (k_gram2_finish)."""
+    n = G2.shape[0]
+    E = G2 - np.eye(n)
+    if not np.all(np.abs(E) <= ORTH_MAX / n):
+        return None, None, False, False
+    if np.all(np.abs(E) <= FIRST_ORDER_MAX):
+        U = np.triu(E, 1) + np.diag(np.diag(E)) / 2
+        return np.eye(n) + U, np.eye(n) - U, True, True
+    R2, ok = cholesky_upper(G2)
+    return R2, (inverse_operand(R2) if ok else None), ok, False
+
+
 def wide_panel(P, kappa_max=KAPPA_MAX):
     """Returns (H, alpha, ok): H in the reference's storage; ok False when a guard refuses the panel (non-positive or
-    non-finite Cholesky pivot, ||D R1^{-1}||_F > kappa_max, or the first pass left ||Q1'Q1 - I|| > 1/4) — the driver then
+    non-finite Cholesky pivot, conditioning estimate > kappa_max, or the first pass left ||Q1'Q1 - I|| > 1/4) — the driver then
     redoes the panel with the 32-column chain.  The guards are invariant under column scaling."""
     P = np.array(P, dtype=np.float64)
     m, n = P.shape
-    assert m >= n
+    assert m >= n and n % BS == 0
     R1, ok = cholesky_upper(P.T @ P)
     if not ok:
         return None, None, False
-    X1 = triu_inverse(R1)
-    if not (kappa_estimate(R1, X1) <= kappa_max):
+    Z1 = inverse_operand(R1)
+    if not (kappa_estimate(R1, Z1) <= kappa_max):
         return None, None, False
-    Q1 = P @ X1
-    G2 = Q1.T @ Q1
-    if not np.all(np.abs(G2 - np.eye(n)) <= ORTH_MAX / n):
-        return None, None, False
-    R2, ok = cholesky_upper(G2)
+    Q1 = solve_right(P, Z1)
+    R2, Z2, ok, _ = second_pass(Q1.T @ Q1)
     if not ok:
         return None, None, False
-    X2 = triu_inverse(R2)
     Rt = np.triu(R2 @ R1)                                   # k_trimm128
-    Wt, Sg, Ud = signed_lu(Q1[:n] @ X2)                     # k_vpk_rmul on the top chunks, k_hr128
+    Wt, Sg, Ud = signed_lu(solve_right(Q1[:n], Z2))         # k_vpk_rmul on the top chunks, k_hr128
     rsq = 1.0 / np.sqrt(Ud)
     sq = Ud * rsq
     cl = -Sg / Ud
     Rr = np.diag(sq) + (cl * sq)[:, None] * np.triu(Wt, 1)
-    X3 = np.triu(X2 @ triu_inverse(Rr))                     # k_hr128 (inverse), k_trimm128 (product)
+    Z23 = inverse_operand(np.triu(Rr @ R2))                 # k_trimm_z
     H = np.zeros((m, n))
-    H[n:] = Q1[n:] @ X3                                     # k_vpk_rmul with the output to user storage
+    H[n:] = solve_right(Q1[n:], Z23)                        # k_vpk_rmul with the output to user storage
     H[:n] = np.tril(Wt, -1) * rsq[None, :] + np.diag(-Sg * sq) + Sg[:, None] * np.triu(Rt, 1)
     alpha = Sg * np.diag(Rt)
     return H, alpha, True
