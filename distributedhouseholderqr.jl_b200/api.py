@@ -138,24 +138,33 @@ def shutdown_distributed() -> None:
 # --------------------------------------------------------------------------------------------
 # layout helpers
 # --------------------------------------------------------------------------------------------
-def colmajor_empty(m: int, n: int, device="cuda", lda: Optional[int] = None) -> torch.Tensor:
-    """(m, n) float64 tensor stored column-major with leading dimension lda (default m)."""
+def colmajor_empty(m: int, n: int, device="cuda", lda: Optional[int] = None, dtype=torch.float64) -> torch.Tensor:
+    """(m, n) float64 (or complex128) tensor stored column-major with leading dimension lda (default m)."""
     lda = max(int(lda or m), 1)
-    base = torch.empty((max(n, 0), lda), dtype=torch.float64, device=device)
+    base = torch.empty((max(n, 0), lda), dtype=dtype, device=device)
     return base.t()[:m, :]
 
 
 def to_colmajor(x, device="cuda") -> torch.Tensor:
-    t = torch.as_tensor(x, dtype=torch.float64)
-    out = colmajor_empty(t.shape[0], t.shape[1], device)
+    t = torch.as_tensor(x)
+    t = t.to(torch.complex128 if t.is_complex() else torch.float64)
+    out = colmajor_empty(t.shape[0], t.shape[1], device, dtype=t.dtype)
     out.copy_(t)
     return out
 
 
+def _sfx(t: torch.Tensor) -> str:
+    """C-ABI suffix for the element type: Float64 -> f64, ComplexF64 -> c64 (the reference's two element types, T:43)."""
+    if t.dtype == torch.float64:
+        return "f64"
+    if t.dtype == torch.complex128:
+        return "c64"
+    raise TypeError("Float64 or ComplexF64 only (float64 / complex128), like the reference's tests (T:43)")
+
+
 def _lda(A: torch.Tensor) -> int:
     m, n = A.shape
-    if A.dtype != torch.float64:
-        raise TypeError("float64 only (the reference's ComplexF64 path is out of scope, SURVEY 8f)")
+    _sfx(A)
     if m > 1 and A.stride(0) != 1:
         raise ValueError("matrix must be column-major: stride(0) == 1 (see colmajor_empty/to_colmajor)")
     lda = A.stride(1) if n > 1 else max(m, 1)
@@ -168,8 +177,10 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def alphafactor(x: float) -> float:
-    """alphafactor(x::Real) = -sign(x) (S:8)."""
+def alphafactor(x):
+    """alphafactor(x::Real) = -sign(x) (S:8);  alphafactor(x::Complex) = -exp(im * angle(x)) (S:9)."""
+    if isinstance(x, complex) or np.iscomplexobj(x):
+        return complex(-np.exp(1j * np.angle(x)))
     return -float(np.sign(x))
 
 
@@ -279,9 +290,15 @@ def householder_(A, alpha, nb: int = 0, handle: Optional[Handle] = None):
     loc, n, col0, h = _dev_args(A)
     h = handle or h
     m = loc.shape[0]
+    if alpha.dtype != loc.dtype:
+        raise TypeError("alpha must have the element type of A")
     with torch.cuda.device(loc.device):
-        _lib.call("dhqr_qr_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
-                  C.c_void_p(alpha.data_ptr()), int(nb), _stream_ptr(loc.device))
+        if _sfx(loc) == "c64":
+            _lib.call("dhqr_qr_c64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+                      C.c_void_p(alpha.data_ptr()), _stream_ptr(loc.device))
+        else:
+            _lib.call("dhqr_qr_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+                      C.c_void_p(alpha.data_ptr()), int(nb), _stream_ptr(loc.device))
     return A, alpha
 
 
@@ -300,7 +317,7 @@ def qr_(A, nb: int = 0, handle: Optional[Handle] = None) -> DistributedHousehold
         return DistributedHouseholderQRStruct(A, alpha, h)
     loc, n, _, h = _dev_args(A)
     h = handle or h
-    alpha = torch.zeros(n, dtype=torch.float64, device=loc.device)            # S:302 / S:307
+    alpha = torch.zeros(n, dtype=loc.dtype, device=loc.device)                # S:302 / S:307
     householder_(A, alpha, nb, h)                                             # S:313
     return DistributedHouseholderQRStruct(A, alpha, h)
 
@@ -314,23 +331,16 @@ def solve_householder_(b: torch.Tensor, A, alpha: torch.Tensor, handle: Optional
     loc, n, col0, h = _dev_args(A)
     h = handle or h
     m = loc.shape[0]
-    if b.dim() == 1:
-        ldb, nrhs = max(m, 1), 1
-        if not b.is_contiguous():
-            raise ValueError("b must be contiguous")
-    else:
-        ldb, nrhs = _lda(b), b.shape[1]
-    if b.shape[0] != m:
-        raise ValueError("b has the wrong number of rows")
+    ldb, nrhs = _rhs_args(b, m, loc.dtype)
     with torch.cuda.device(loc.device):
-        _lib.call("dhqr_solve_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+        _lib.call("dhqr_solve_" + _sfx(loc), h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
                   C.c_void_p(alpha.data_ptr()), C.c_void_p(b.data_ptr()), ldb, nrhs, _stream_ptr(loc.device))
     return b[:n]
 
 
-def _rhs_args(b: torch.Tensor, m: int):
-    if b.dtype != torch.float64:
-        raise TypeError("b must be float64")
+def _rhs_args(b: torch.Tensor, m: int, dtype=torch.float64):
+    if b.dtype != dtype:
+        raise TypeError(f"b must have the element type of A ({dtype})")
     if b.dim() not in (1, 2) or b.shape[0] != m:
         raise ValueError(f"b must have {m} rows (a length-m vector or an (m, k) column-major block)")
     if b.dim() == 1:
@@ -344,22 +354,24 @@ def _apply(fn: str, b: torch.Tensor, A, handle: Optional[Handle]) -> torch.Tenso
     loc, n, col0, h = _dev_args(A)
     h = handle or h
     m = loc.shape[0]
-    ldb, nrhs = _rhs_args(b, m)
+    ldb, nrhs = _rhs_args(b, m, loc.dtype)
     with torch.cuda.device(loc.device):
-        _lib.call(fn, h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+        _lib.call(fn + _sfx(loc), h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
                   C.c_void_p(b.data_ptr()), ldb, nrhs, _stream_ptr(loc.device))
     return b
 
 
 def apply_qt_(b: torch.Tensor, A, handle: Optional[Handle] = None) -> torch.Tensor:
     """_solve_householder1! (S:226-242): b <- H_n ... H_1 b = Q'b, in place (b: length m, or (m, k) column-major)."""
-    return _apply("dhqr_apply_qt_f64", b, A, handle)
+    return _apply("dhqr_apply_qt_", b, A, handle)
 
 
 def apply_q_(b: torch.Tensor, A, handle: Optional[Handle] = None) -> torch.Tensor:
     """b <- H_1 ... H_n b = Q b, in place: the inverse of apply_qt_ (the reference never forms Q; this exposes the
     factorisation as an operator)."""
-    return _apply("dhqr_apply_q_f64", b, A, handle)
+    if (A.local if isinstance(A, ColumnBlockMatrix) else A).dtype != torch.float64:
+        raise TypeError("apply_q_ is Float64 only")
+    return _apply("dhqr_apply_q_", b, A, handle)
 
 
 def backsolve_(b: torch.Tensor, A, alpha: torch.Tensor, handle: Optional[Handle] = None) -> torch.Tensor:
@@ -367,9 +379,9 @@ def backsolve_(b: torch.Tensor, A, alpha: torch.Tensor, handle: Optional[Handle]
     loc, n, col0, h = _dev_args(A)
     h = handle or h
     m = loc.shape[0]
-    ldb, nrhs = _rhs_args(b, m)
+    ldb, nrhs = _rhs_args(b, m, loc.dtype)
     with torch.cuda.device(loc.device):
-        _lib.call("dhqr_backsolve_f64", h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
+        _lib.call("dhqr_backsolve_" + _sfx(loc), h.raw, m, n, col0, loc.shape[1], C.c_void_p(loc.data_ptr()), _lda(loc),
                   C.c_void_p(alpha.data_ptr()), C.c_void_p(b.data_ptr()), ldb, nrhs, _stream_ptr(loc.device))
     return b[:n]
 
@@ -387,22 +399,26 @@ def ldiv(H: DistributedHouseholderQRStruct, b):
         return x
     loc = H.A.local if isinstance(H.A, ColumnBlockMatrix) else H.A
     if b.dim() == 1:
-        s = b.to(device=loc.device, dtype=torch.float64).clone()                  # S:318
+        s = b.to(device=loc.device, dtype=loc.dtype).clone()                      # S:318
     else:
         s = to_colmajor(b, device=loc.device)
     x = solve_householder_(s, H.A, H.α, H.handle)                                # S:319
     return x.clone()                                                              # S:320
 
 
-def partialdot(a: torch.Tensor, b: torch.Tensor, rng, handle: Optional[Handle] = None) -> float:
-    """partialdot(a, b, is, ::Type{<:Real}) (S:42-49); ``rng`` is a 0-based Python range."""
+def partialdot(a: torch.Tensor, b: torch.Tensor, rng, handle: Optional[Handle] = None):
+    """partialdot(a, b, is, ::Type{<:Real}) (S:42-49) / ::Type{<:Complex} (S:51-59: sum conj(a[i]) b[i]); ``rng`` is a
+    0-based Python range."""
     h = handle or default_handle(a.device.index)
+    if a.dtype != b.dtype:
+        raise TypeError("a and b must have the same element type")
     i0, i1 = (rng.start, rng.stop) if len(rng) else (0, 0)
-    out = torch.zeros(1, dtype=torch.float64, device=a.device)
+    out = torch.zeros(1, dtype=a.dtype, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.call("dhqr_partialdot_f64", h.raw, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), i0, i1,
+        _lib.call("dhqr_partialdot_" + _sfx(a), h.raw, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), i0, i1,
                   C.c_void_p(out.data_ptr()), _stream_ptr(a.device))
-    return float(out.item())
+    v = out.item()
+    return complex(v) if a.is_complex() else float(v)
 
 
 def fill_uniform_(A: torch.Tensor, seed: int, i0: int = 0, j0: int = 0, handle: Optional[Handle] = None) -> torch.Tensor:

@@ -15,6 +15,7 @@
 
 #include "dhqr_kernels.cuh"
 #include "dhqr_wide.cuh"
+#include "dhqr_complex.cuh"
 
 using namespace dhqr;
 
@@ -117,6 +118,7 @@ struct dhqr_context {
     double* linv_ring[3] = {nullptr, nullptr, nullptr};               // T' of the outer panels in flight (look-ahead)
     cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
+    cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
     int lookahead = 1;
     int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
     std::vector<float> la_times;                                        // [k][3]: panel k done (hp), next k signalled (st), bulk k done (st), ms since start
@@ -127,6 +129,7 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
+    int cvy_persist = 1;                                                // 128-wide gemm_cvy: persistent CTAs (the operand pipeline never drains)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
     int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     int tail_cols = 0;                                                  // trailing width below which the chain is considered critical
@@ -177,7 +180,7 @@ static constexpr int G2_BM = 128, G2_BN = YT;               // gemm_cvy: 128 x 6
 
 static size_t smem_g1(int nbp, int bn) { return (size_t)2 * (nbp + bn) * LD1 * 8 + 4 * 8; }
 static size_t smem_g2() { return (size_t)2 * (2 * KC * LD1 + G2_BN * LDK) * 8 + 4 * 8; }
-static size_t smem_tinv(int nbp) { return ((size_t)nbp * (nbp + 1) + 4 * 32 * 33) * 8; }
+static size_t smem_tinv(int nbp) { return ((size_t)nbp * (nbp + 1) + 4 * 32 * 33 + (nbp == 128 ? 64 * 65 : 0)) * 8; }
 static size_t smem_ymake(int nbp) { return ((size_t)nbp * nbp + YCOLS * nbp) * 8; }
 
 #define K_G1_128 k_gemm_vta<128, G1_BN, 4, 2, G1_NPW>
@@ -196,6 +199,8 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
+    CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
     CU(cudaFuncSetAttribute(k_tinv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(32)));
     CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
@@ -390,7 +395,10 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g2.sm_ticket = c->cvy_stagger ? c->sm_ticket : nullptr; g2.first_wave = 2 * c->sms; g2.stagger_cycles = 5200 * g2.nkq;
     g2.ctl = c->wctl; g2.gate = gate;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
-    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_defer) K_G2D<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
+    g2.tiles_m = (int)grid2.x; g2.tiles_n = (int)grid2.y;
+    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_persist)
+        k_gemm_cvy_p<<<std::min<int>(g2.tiles_m * g2.tiles_n, 2 * c->sms), 9 * 32, smem_g2(), st>>>(g2);
+    else if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_defer) K_G2D<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
     TRY(post(c, st, small ? "k_gemm_cvy32" : "k_gemm_cvy128", 2.0 * (double)rows * (small ? 32 : nbp) * (double)ncols));
@@ -669,18 +677,36 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
     const int maxch = c->vta_max_chunks;   // 0: no cap on the chunks per gemm_vta CTA (short CTAs did not help the chain)
     // local intersection of the global column range [a, b) -> pointer + count
     auto clip = [&](int64_t a, int64_t b, int64_t& lo, int64_t& hi) { lo = std::max(a, col0); hi = std::min(b, lend); return hi > lo; };
-    // publish panel k (already factored on its owner into vpk[k%3]) to every rank; hp stream
+    // publish panel k (already factored on its owner into vpk[k%3]) to every rank.  The collectives run on their own stream:
+    // the owner's chain goes on with panel k+1 (it has V_k already) while V_k travels; the other ranks pick it up through
+    // evPanel[k].  The comm stream first waits for everything queued on hp so far: on the owner that is the factorisation of
+    // panel k, on every rank the last reads of the ring slot's previous occupant V_{k-3}.
+    cudaStream_t cs = c->comm_stream;
+    std::vector<cudaEvent_t> evHp(K, nullptr);
     auto publish = [&](int k) -> int {
         if (c->nranks > 1) {
             const PanelGeom g = panel_geom(panels[k], m);
             double* v = c->vpk2[k % 3];
-            NC(g_nccl.Broadcast(v, v, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, panels[k].owner, c->comm, hp));
-            NC(g_nccl.Broadcast(alpha + panels[k].c, alpha + panels[k].c, (size_t)panels[k].kb, ncclFloat64, panels[k].owner, c->comm, hp));
-            k_wide_note<<<1, 32, 0, hp>>>(c->wctl, v + KC1, k);   // the owner's verdict on the panel arrived with the buffer
-            TRY(post(c, hp, "k_wide_note"));
+            CU(cudaEventCreateWithFlags(&evHp[k], cudaEventDisableTiming));
+            CU(cudaEventRecord(evHp[k], hp));
+            CU(cudaStreamWaitEvent(cs, evHp[k], 0));
+            NC(g_nccl.Broadcast(v, v, (size_t)(g.vrows / KC1) * VPK_CHUNK, ncclFloat64, panels[k].owner, c->comm, cs));
+            NC(g_nccl.Broadcast(alpha + panels[k].c, alpha + panels[k].c, (size_t)panels[k].kb, ncclFloat64, panels[k].owner, c->comm, cs));
+            k_wide_note<<<1, 32, 0, cs>>>(c->wctl, v + KC1, k);   // the owner's verdict on the panel arrived with the buffer
+            TRY(post(c, cs, "k_wide_note"));
+            CU(cudaEventRecord(evPanel[k], cs));
+        } else {
+            CU(cudaEventRecord(evPanel[k], hp));
         }
-        CU(cudaEventRecord(evPanel[k], hp));
         return 0;
+    };
+    // V_k is usable on stream s: the owner has it once its own chain got there (hp order / evHp), the others once it arrived
+    auto wait_panel = [&](cudaStream_t s, int k) {
+        if (c->nranks > 1 && c->rank == panels[k].owner) {
+            if (s != hp) cudaStreamWaitEvent(s, evHp[k], 0);
+        } else {
+            cudaStreamWaitEvent(s, evPanel[k], 0);
+        }
     };
     int rc = 0;
     cudaEvent_t fork = nullptr, hpdone = nullptr;
@@ -705,9 +731,14 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             double* lk = c->linv_ring[k % 3];
             bool haveT = false;                                          // T'_k in lk (this rank)
             if (k + 1 < K) {
-                // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2
-                if (k - 2 >= K0) cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
+                // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2 (and, on the owner of panel k-2,
+                // by its broadcast)
+                if (k - 2 >= K0) {
+                    cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
+                    if (c->nranks > 1) cudaStreamWaitEvent(hp, evPanel[k - 2], 0);
+                }
                 if (c->rank == panels[k + 1].owner) {
+                    wait_panel(hp, k);
                     if (clip(t0, t1, lo, hi)) {
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
                                                         lda, (int)(hi - lo), 0, false, lk, k + 1))) break;
@@ -728,6 +759,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1
             if (clip(t1, t2, lo, hi)) {
                 if (k - 1 >= K0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
+                wait_panel(hp, k);
                 const bool hadT = haveT;
                 if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
                                                 (int)(hi - lo), 0, haveT, lk, k + 1))) break;
@@ -735,7 +767,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                 if (!hadT) cudaEventRecord(evNext[k], hp);               // T'_k came from this apply
             }
             if (!haveT) cudaEventRecord(evNext[k], hp);                  // keep the event defined (timeline tracing)
-            cudaStreamWaitEvent(st, evPanel[k], 0);
+            wait_panel(st, k);
             if (clip(t2, lend, lo, hi)) {
                 if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);
                 if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
@@ -745,7 +777,11 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         }
         if (rc) break;
         c->bulk_wide = true;
-        cudaStreamWaitEvent(st, evPanel[K - 1], 0);                // join: alpha and the last panel come from hp
+        cudaStreamWaitEvent(st, evPanel[K - 1], 0);                // join: alpha and the last panel come from hp / the comm stream
+        if (c->nranks > 1) {
+            cudaEventRecord(evHp[K - 1], hp);                      // (re-recorded: everything queued on hp)
+            cudaStreamWaitEvent(st, evHp[K - 1], 0);
+        }
         if (c->la_trace) {
             cudaStreamSynchronize(st);
             cudaStreamSynchronize(hp);
@@ -761,8 +797,12 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
     if (rc && cudaEventCreateWithFlags(&hpdone, cudaEventDisableTiming) == cudaSuccess) {
         cudaEventRecord(hpdone, hp);
         cudaStreamWaitEvent(st, hpdone, 0);
+        cudaEventRecord(hpdone, cs);
+        cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventDestroy(hpdone);
     }
+    for (cudaEvent_t e : evHp)
+        if (e) cudaEventDestroy(e);
     // events may be destroyed once recorded/waited on: the work they order is already enqueued
     if (fork) cudaEventDestroy(fork);
     for (int k = K0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
@@ -929,6 +969,7 @@ static int create_common(dhqr_handle* h, int device) {
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&c->hp_hi, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&c->hp_lo, cudaStreamNonBlocking, lo));
+        CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
         c->hp_stream = c->hp_hi;
     }
     *h = c;
@@ -977,6 +1018,7 @@ int dhqr_destroy(dhqr_handle c) {
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -1011,6 +1053,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "cvy_persist")) {
+        c->cvy_persist = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_defer")) {
         c->cvy_defer = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_stagger")) {
@@ -1212,6 +1256,119 @@ int dhqr_solve_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int
                    int64_t lda, const double* d_alpha, double* d_b, int64_t ldb, int nrhs, void* stream) {
     TRY(dhqr_apply_qt_f64(c, m, n_global, col0, n_local, dA, lda, d_b, ldb, nrhs, stream));   // S:288
     return dhqr_backsolve_f64(c, m, n_global, col0, n_local, dA, lda, d_alpha, d_b, ldb, nrhs, stream);   // S:291
+}
+
+// ---- ComplexF64 (S:9, S:51-59, S:162-196; test/runtests.jl:43) -------------------------------------------------------
+// Panels of 64 complex columns: complex column-by-column panel, then the trailing update as the REAL block reflector of the
+// 128 vectors [v_r, v_i] on the real view of the matrix (dhqr_complex.cuh).  Single GPU.
+static int check_complex(dhqr_context* c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const void* A, int64_t lda) {
+    TRY(check_common(c, m, n_global, col0, n_local, A, lda));
+    if (c->nranks != 1 || col0 != 0 || n_local != n_global) return set_err(-1, "the ComplexF64 path is single-GPU (col0 = 0, n_local = n_global)");
+    return 0;
+}
+
+static int pack_complex_panel(dhqr_context* c, cudaStream_t st, const double2* P, int64_t lda, int64_t mpc, int kb, int64_t vrows) {
+    dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), NBMAX);
+    k_pack_c<<<grid, 256, 0, st>>>(P, lda, mpc, kb, c->vpk2[0], 0, vrows);
+    return post(c, st, "k_pack_c");
+}
+
+int dhqr_qr_c64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, void* dA, int64_t lda, void* d_alpha,
+                void* stream) {
+    TRY(check_complex(c, m, n_global, col0, n_local, dA, lda));
+    if (n_global > 0 && !d_alpha) return set_err(-8, "null alpha");
+    if (n_global == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_global;
+    TRY(ensure_workspace(c, 2 * m, n));
+    double2* A = (double2*)dA;
+    double2* alpha = (double2*)d_alpha;
+    for (int64_t c0 = 0; c0 < n; c0 += CPW) {
+        const int kb = (int)std::min<int64_t>(CPW, n - c0);
+        double2* P = A + c0 * lda + c0;
+        const int64_t mpc = m - c0;
+        for (int j = 0; j < kb; ++j) {                       // S:127-144 restricted to the panel
+            double2* col = P + (int64_t)j * lda + j;
+            k_house1_c<<<1, 1024, 0, st>>>(col, mpc - j, alpha + c0 + j);
+            TRY(post(c, st, "k_house1_c"));
+            if (j + 1 < kb) {
+                k_apply1_c<<<kb - j - 1, 256, 0, st>>>(col, mpc - j, col + lda, lda, kb - j - 1);
+                TRY(post(c, st, "k_apply1_c"));
+            }
+        }
+        const int64_t t0 = c0 + kb;
+        if (t0 < n) {                                        // S:198-213 for the columns right of the panel, blocked
+            const int64_t rows = 2 * mpc, vrows = rup(rows, 128);
+            TRY(pack_complex_panel(c, st, P, lda, mpc, kb, vrows));
+            TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, NBMAX, rows, 0, (double*)(A + t0 * lda + c0), 2 * lda, (int)(n - t0)));
+        }
+    }
+    return 0;
+}
+
+int dhqr_apply_qt_c64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const void* dA, int64_t lda,
+                      void* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(check_complex(c, m, n_global, col0, n_local, dA, lda));
+    if (nrhs < 0) return set_err(-10, "nrhs < 0");
+    if (nrhs > 0 && !d_b) return set_err(-8, "null b");
+    if (ldb < std::max<int64_t>(1, m)) return set_err(-9, "ldb < max(1,m)");
+    if (n_global == 0 || nrhs == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(c, 2 * m, std::max<int64_t>(n_global, nrhs)));
+    const double2* A = (const double2*)dA;
+    double2* b = (double2*)d_b;
+    for (int64_t c0 = 0; c0 < n_global; c0 += CPW) {         // S:232-242, panel by panel
+        const int kb = (int)std::min<int64_t>(CPW, n_global - c0);
+        const int64_t mpc = m - c0, rows = 2 * mpc, vrows = rup(rows, 128);
+        TRY(pack_complex_panel(c, st, A + c0 * lda + c0, lda, mpc, kb, vrows));
+        TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, NBMAX, rows, 0, (double*)(b + c0), 2 * ldb, nrhs));
+    }
+    return 0;
+}
+
+int dhqr_backsolve_c64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const void* dA, int64_t lda,
+                       const void* d_alpha, void* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(check_complex(c, m, n_global, col0, n_local, dA, lda));
+    if (n_global > 0 && !d_alpha) return set_err(-8, "null alpha");
+    if (nrhs < 0) return set_err(-11, "nrhs < 0");
+    if (nrhs > 0 && !d_b) return set_err(-9, "null b");
+    if (ldb < std::max<int64_t>(1, m)) return set_err(-10, "ldb < max(1,m)");
+    if (n_global == 0 || nrhs == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_global;
+    TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)2 * n * nrhs));
+    const double2* A = (const double2*)dA;
+    double2* x = (double2*)c->xbuf;
+    for (int64_t o = ((n - 1) / BS_BLK) * BS_BLK; o >= 0; o -= BS_BLK) {     // S:260: i = n:-1:1, by blocks
+        const int bs = (int)std::min<int64_t>(BS_BLK, n - o);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((o + 255) / 256, 2 * c->sms));
+        k_backsolve_step_c<<<grid, 256, 0, st>>>(A + o * lda, lda, (const double2*)d_alpha, (double2*)d_b, ldb, nrhs, x, n, o, bs);
+        TRY(post(c, st, "k_backsolve_step_c"));
+    }
+    CU(cudaMemcpy2DAsync(d_b, (size_t)ldb * 16, x, (size_t)n * 16, (size_t)n * 16, nrhs, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dhqr_solve_c64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const void* dA, int64_t lda,
+                   const void* d_alpha, void* d_b, int64_t ldb, int nrhs, void* stream) {
+    TRY(dhqr_apply_qt_c64(c, m, n_global, col0, n_local, dA, lda, d_b, ldb, nrhs, stream));                   // S:288
+    return dhqr_backsolve_c64(c, m, n_global, col0, n_local, dA, lda, d_alpha, d_b, ldb, nrhs, stream);       // S:291
+}
+
+int dhqr_partialdot_c64(dhqr_handle c, const void* d_a, const void* d_b, int64_t i0, int64_t i1, void* d_out, void* stream) {
+    if (!c) return set_err(-1, "null handle");
+    if (!d_a) return set_err(-2, "null a");
+    if (!d_b) return set_err(-3, "null b");
+    if (i0 < 0) return set_err(-4, "i0 < 0");
+    if (i1 < i0) return set_err(-5, "i1 < i0");
+    if (!d_out) return set_err(-6, "null out");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_partialdot_c<<<1, 1024, 0, st>>>((const double2*)d_a, (const double2*)d_b, i0, i1, (double2*)d_out);
+    return post(c, st, "k_partialdot_c");
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------

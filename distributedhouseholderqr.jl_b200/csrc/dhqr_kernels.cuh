@@ -310,6 +310,7 @@ struct GemmCvyArgs {
     int stagger_cycles; // delay of the odd-ticket CTA of an SM in the first wave
     const WideCtl* ctl; // speculative panel chain: skip when a panel below `gate` was refused (may be null)
     int gate;
+    int tiles_m, tiles_n;   // persistent variant: row tiles (of 128) x column tiles (of 64)
 };
 
 // DEFER (requires nkq == MI, i.e. the 128-wide update with 32-row warp tiles): the accumulators start at zero and the C tile is
@@ -486,6 +487,214 @@ __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArg
 }
 
 // ------------------------------------------------------------------------------------------------
+// gemm_cvy_p: the 128-wide update C += V Y with PERSISTENT CTAs (2 per SM, each walking over its tiles).  Same tile, same warp
+// layout and the same deferred C reads as k_gemm_cvy<4, 2, true>; what changes is that the TMA producer warp runs ahead across
+// tile boundaries, so the operand pipeline of a CTA never drains: a one-tile CTA pays launch + barrier set-up + the first two
+// stage fills (about 4 of its 21 microseconds, profiles/r01_prof_cvy_ncu.txt) before its first DMMA.
+//   tile t -> row tile t % tiles_m, column tile t / tiles_m: consecutive tiles of a CTA share the Y block (L2).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_p(GemmCvyArgs a) {
+    constexpr int BM = 128, BN = YT, WM = 4, WN = 2, NCW = WM * WN, STAGES = 2;
+    constexpr int WTM = BM / WM, WTN = BN / WN;
+    constexpr int MI = WTM / 8, NJ = WTN / 8, NH = NJ / 2;
+    constexpr int VH = KC * LD1;   // doubles per 64-row x 32-col slice
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][2][KC][LD1]
+    double* sY = sV + STAGES * 2 * VH;                   // [STAGES][BN][LDK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sY + STAGES * BN * LDK);
+    uint64_t* empty = full + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (wide_gate_closed(a.ctl, a.gate)) return;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int ntiles = a.tiles_m * a.tiles_n;
+
+    if (warp == NCW) {
+        // ===== TMA producer warp: (tile, k-stage) pairs back to back =====
+        if (lane == 0) {
+            int g = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int bx = t % a.tiles_m, by = t / a.tiles_m;
+                const double* v0 = a.vpk + (int64_t)(2 * bx) * VPK_CHUNK + (int64_t)a.voff * LD1;
+                const double* y0 = a.ypk + (int64_t)by * a.nkq_alloc * (BN * LDK);
+                for (int it = 0; it < MI; ++it, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * VH + BN * LDK) * 8));
+                    double* dV = sV + (size_t)s * 2 * VH;
+                    bulk_g2s(dV, v0 + (int64_t)it * VH, VH * 8, &full[s]);
+                    bulk_g2s(dV + VH, v0 + VPK_CHUNK + (int64_t)it * VH, VH * 8, &full[s]);
+                    bulk_g2s(sY + (size_t)s * BN * LDK, y0 + (int64_t)it * (BN * LDK), BN * LDK * 8, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== DMMA consumer warps =====
+    const int wm = warp / WN, wn = warp % WN;
+    const int fragA = (lane & 3) * LD1 + (lane >> 2);
+    const int fragB = (lane >> 2) * LDK + (lane & 3);
+    const double* v0s = sV + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
+    const double* y0s = sY + wn * WTN * LDK + fragB;
+    int g = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int bx = t % a.tiles_m, by = t / a.tiles_m;
+        const int64_t rbase = (int64_t)bx * BM + wm * WTM + (lane >> 2);
+        const int cbase = by * BN + wn * WTN + (lane & 3) * 2;
+        double acc[MI][NJ][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        auto load_half = [&](int i, int j0, double (&dst)[NH][2]) {
+            const int64_t row = rbase + i * 8;
+            const bool rok = row >= a.row_lo && row < a.rows;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+                const int col = cbase + (j0 + j) * 8;
+                const double* p = a.C + (int64_t)col * a.ldc + row;
+                dst[j][0] = (rok && col < a.ncols) ? *p : 0.0;
+                dst[j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
+            }
+        };
+        auto mma_steps = [&](int s, int k_lo, int k_hi) {
+            const double* v = v0s + (size_t)s * 2 * VH;
+            const double* y = y0s + (size_t)s * BN * LDK;
+#pragma unroll
+            for (int kk = k_lo; kk < k_hi; ++kk) {
+                double af[MI], bf[NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LD1 + i * 8];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bf[j] = y[j * 8 * LDK + kk * 4];
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        };
+#pragma unroll 1
+        for (int it = 0; it < MI; ++it, ++g) {                   // one 8-row block of C per k-stage, in two halves
+            const int s = g % STAGES;
+            double cpre[NH][2];
+            load_half(it, 0, cpre);
+            mbar_wait(&full[s], (g / STAGES) & 1);
+            release_prev_stage(empty, g, STAGES, lane);
+            mma_steps(s, 0, KC / 8);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+                if (i == it) {
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        acc[i][j][0] += cpre[j][0];
+                        acc[i][j][1] += cpre[j][1];
+                    }
+                }
+            load_half(it, NH, cpre);
+            mma_steps(s, KC / 8, KC / 4);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+                if (i == it) {
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        acc[i][NH + j][0] += cpre[j][0];
+                        acc[i][NH + j][1] += cpre[j][1];
+                    }
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int64_t row = rbase + i * 8;
+            const bool rok = row >= a.row_lo && row < a.rows;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int col = cbase + j * 8;
+                double* p = a.C + (int64_t)col * a.ldc + row;
+                if (rok && col < a.ncols) *p = acc[i][j][0];
+                if (rok && col + 1 < a.ncols) *(p + a.ldc) = acc[i][j][1];
+            }
+        }
+    }
+    // the last stage of the last tile is never released: nobody waits for it
+}
+
+constexpr int WP = 128;            // wide panel width
+constexpr int WLD = WP + 1;        // leading dimension of the row-major 128 x 128 work matrices in shared memory
+
+// ------------------------------------------------------------------------------------------------
+// Inverse of an upper triangular 32 x 32 block by ONE warp (lane = column of the inverse, back substitution in registers;
+// every lane runs the same 496 multiply-adds, the entries of R are broadcast loads).  R: row-major, leading dimension ldr;
+// dinv = 1 / diag(R) or null; D: row-major 32 x 32 with leading dimension LDD (zeros below the diagonal).
+// ------------------------------------------------------------------------------------------------
+constexpr int LDD = 33;   // leading dimension of an inverted 32 x 32 block in shared memory
+__device__ __forceinline__ void triu_inv32_warp(const double* R, int ldr, const double* dinv, double* D, int lane) {
+    double x[32];
+#pragma unroll
+    for (int i = 31; i >= 0; --i) {
+        double s = i == lane ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = i + 1; p < 32; ++p) s -= R[i * ldr + p] * x[p];       // x[p] == 0 for p > lane
+        const double di = dinv ? dinv[i] : 1.0 / R[i * ldr + i];
+        x[i] = i <= lane ? s * di : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[i * LDD + lane] = x[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-place inverse of the upper triangle of A (row-major, leading dimension WLD, 128 x 128), 16 warps: the four 32 x 32
+// diagonal blocks by triu_inv32_warp, then two levels of X12 = -X11 (R12 X22) on the fp64 tensor pipe (the scalar form is
+// bound by its two shared-memory loads per multiply-add).  dinv = 1 / diag or null (diagonal read from A).  The strict lower
+// triangle of A must be ZERO inside the diagonal 32 x 32 blocks (the tensor-pipe tiles on the diagonal read it).
+// T: scratch of 4 * 32 * LDD doubles (diagonal blocks), T2: scratch of 64 * 65 doubles (R12 X22).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void triu_inv128_mma(double* A, const double* dinv, double* T, double* T2, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < 4) triu_inv32_warp(A + (32 * warp) * WLD + 32 * warp, WLD, dinv ? dinv + 32 * warp : nullptr, T + warp * 32 * LDD, lane);
+    __syncthreads();
+    for (int e = tid; e < 4096; e += 512) {
+        const int b = e >> 10, i = (e >> 5) & 31, c = e & 31;
+        if (i <= c) A[(32 * b + i) * WLD + 32 * b + c] = T[b * 32 * LDD + i * LDD + c];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int bs = 32; bs < WP; bs *= 2) {
+        const int nt = bs / 8, ntile = nt * nt, npairs = WP / (2 * bs), ld2 = bs + 1;
+        // Tm = R12 X22 (X22 upper triangular: k <= column)
+        for (int idx = warp; idx < npairs * ntile; idx += 16) {
+            const int pi = idx / ntile, tt = idx % ntile, ti = tt / nt, tj = tt % nt, o = pi * 2 * bs;
+            const double* pa = A + (o + 8 * ti + (lane >> 2)) * WLD + o + bs + (lane & 3);          // R12(i, k)
+            const double* pb = A + (o + bs + (lane & 3)) * WLD + o + bs + 8 * tj + (lane >> 2);      // X22(k, j)
+            double c0 = 0.0, c1 = 0.0;
+            for (int k4 = 0; k4 < 2 * (tj + 1); ++k4) dmma(c0, c1, pa[4 * k4], pb[4 * k4 * WLD]);
+            double* pt = T2 + pi * bs * ld2 + (8 * ti + (lane >> 2)) * ld2 + 8 * tj + 2 * (lane & 3);
+            pt[0] = c0;
+            pt[1] = c1;
+        }
+        __syncthreads();
+        // X12 = -X11 Tm (X11 upper triangular: k >= row)
+        for (int idx = warp; idx < npairs * ntile; idx += 16) {
+            const int pi = idx / ntile, tt = idx % ntile, ti = tt / nt, tj = tt % nt, o = pi * 2 * bs;
+            const double* pa = A + (o + 8 * ti + (lane >> 2)) * WLD + o + (lane & 3);               // X11(i, k)
+            const double* pb = T2 + pi * bs * ld2 + (lane & 3) * ld2 + 8 * tj + (lane >> 2);         // Tm(k, j)
+            double c0 = 0.0, c1 = 0.0;
+            for (int k4 = 2 * ti; k4 < 2 * nt; ++k4) dmma(c0, c1, pa[4 * k4], pb[4 * k4 * ld2]);
+            double* pc = A + (o + 8 * ti + (lane >> 2)) * WLD + o + bs + 8 * tj + 2 * (lane & 3);
+            pc[0] = -c0;
+            pc[1] = -c1;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // tinv:  Linv = (I + stril(S))^{-1},  S = first NBP ext columns of the reduced Wext.
 //   With |v|^2 = 2 the compact-WY factor obeys T^{-1} = I + striu(V'V), so Linv == T'.
 //   One CTA; 8x8 diagonal blocks by forward substitution, then log2(NBP/8) merge levels
@@ -539,20 +748,38 @@ __device__ __forceinline__ void tinv_core(double* L, double* T, int tid, int nth
 
 template <int NBP>
 __global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv) {
-    constexpr int LDL = NBP + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
-    double* T = L + NBP * LDL;                          // scratch, 4 * 32 * 33 doubles
     const int tid = threadIdx.x;
-    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
-        const int i = e % NBP, j = e / NBP;
-        L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
-    }
-    __syncthreads();
-    tinv_core<NBP>(L, T, tid, blockDim.x);
-    for (int e = tid; e < NBP * NBP; e += blockDim.x) {
-        const int i = e % NBP, j = e / NBP;
-        Linv[e] = (i >= j) ? L[j * LDL + i] : 0.0;
+    if (NBP == WP) {
+        // (I + stril(S))^{-1} = ((I + striu(S'))^{-1})': row r of U = I + striu(S') is column r of S below the diagonal, i.e. a
+        // contiguous run of Ws, and row j of U^{-1} is column j of the result: both transfers are linear in memory
+        double* A = reinterpret_cast<double*>(smem_raw);   // [128][WLD] row-major
+        double* T = A + WP * WLD;                            // 4 * 32 * LDD
+        double* T2 = T + 4 * 32 * LDD;                       // 64 * 65
+        for (int e = tid; e < WP * WP; e += 512) {
+            const int r = e >> 7, cc = e & (WP - 1);
+            A[r * WLD + cc] = cc > r ? Ws[e] : (cc == r ? 1.0 : 0.0);   // zeros below: the 8 x 8 tiles on the diagonal read them
+        }
+        __syncthreads();
+        triu_inv128_mma(A, nullptr, T, T2, tid);
+        for (int e = tid; e < WP * WP; e += 512) {
+            const int j = e >> 7, i = e & (WP - 1);
+            Linv[e] = i >= j ? A[j * WLD + i] : 0.0;
+        }
+    } else {
+        constexpr int LDL = NBP + 1;
+        double* L = reinterpret_cast<double*>(smem_raw);   // [NBP][LDL], element (i,j) at j*LDL + i
+        double* T = L + NBP * LDL;                          // scratch, 4 * 32 * 33 doubles
+        for (int e = tid; e < NBP * NBP; e += blockDim.x) {
+            const int i = e % NBP, j = e / NBP;
+            L[j * LDL + i] = (i > j) ? Ws[e] : 0.0;
+        }
+        __syncthreads();
+        tinv_core<NBP>(L, T, tid, blockDim.x);
+        for (int e = tid; e < NBP * NBP; e += blockDim.x) {
+            const int i = e % NBP, j = e / NBP;
+            Linv[e] = (i >= j) ? L[j * LDL + i] : 0.0;
+        }
     }
 }
 

@@ -27,8 +27,6 @@
 
 namespace dhqr {
 
-constexpr int WP = 128;            // wide panel width
-constexpr int WLD = WP + 1;        // leading dimension of the row-major 128 x 128 work matrices in shared memory
 
 // rmul operand layout of an upper-triangular 128 x 128 matrix X (B operand of vpk <- vpk X): per 32-column block nbk only
 // the rows k < 32 (nbk + 1) are kept,  XL[xl_off(nbk) + (n % 32) * xl_ld(nbk) + k];  every leading dimension is == 4 mod 16
@@ -55,26 +53,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ------------------------------------------------------------------------------------------------
-// Inverse of an upper triangular 32 x 32 block by ONE warp (lane = column of the inverse, back substitution in registers;
-// every lane runs the same 496 multiply-adds, the entries of R are broadcast loads).  R: row-major, leading dimension ldr;
-// dinv = 1 / diag(R) or null; D: row-major 32 x 32 with leading dimension LDD (zeros below the diagonal).
-// ------------------------------------------------------------------------------------------------
-constexpr int LDD = 33;   // leading dimension of an inverted 32 x 32 block in shared memory
-__device__ __forceinline__ void triu_inv32_warp(const double* R, int ldr, const double* dinv, double* D, int lane) {
-    double x[32];
-#pragma unroll
-    for (int i = 31; i >= 0; --i) {
-        double s = i == lane ? 1.0 : 0.0;
-#pragma unroll
-        for (int p = i + 1; p < 32; ++p) s -= R[i * ldr + p] * x[p];       // x[p] == 0 for p > lane
-        const double di = dinv ? dinv[i] : 1.0 / R[i * ldr + i];
-        x[i] = i <= lane ? s * di : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) D[i * LDD + lane] = x[i];
-}
 
 // ------------------------------------------------------------------------------------------------
 // chol128: R = chol(G) (upper) and its blocked inverse operand Z; one CTA of 512 threads.  G: [j * 128 + i] (k_wreduce).

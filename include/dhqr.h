@@ -120,6 +120,25 @@ int dhqr_solve_f64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int
                    const double *dA_local, int64_t lda, const double *d_alpha, double *d_b,
                    int64_t ldb, int nrhs, void *stream);
 
+/* ---- ComplexF64 (the reference's second element type: test/runtests.jl:43; alphafactor(::Complex) S:9, the conjugating
+ * partialdot S:51-59, the complex hotloop! S:162-196).  Matrices and vectors are interleaved (re, im) doubles = Julia
+ * ComplexF64 / C double _Complex; lda, ldb count COMPLEX elements; alpha is complex (length n).  Same storage format:
+ * v scaled to |v|^2 = 2 in the lower trapezoid including the diagonal, H_j = I - v_j v_j^H, diag(R) in alpha.
+ * Single GPU: col0 must be 0 and n_local == n_global.  Stream-ordered, no synchronisation. */
+int dhqr_qr_c64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, void *dA_local,
+                int64_t lda, void *d_alpha, void *stream);
+int dhqr_apply_qt_c64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                      const void *dA_local, int64_t lda, void *d_b, int64_t ldb, int nrhs, void *stream);
+int dhqr_backsolve_c64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                       const void *dA_local, int64_t lda, const void *d_alpha, void *d_b, int64_t ldb,
+                       int nrhs, void *stream);
+int dhqr_solve_c64(dhqr_handle h, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                   const void *dA_local, int64_t lda, const void *d_alpha, void *d_b, int64_t ldb, int nrhs,
+                   void *stream);
+/* partialdot(a, b, is, ::Type{<:Complex}) (S:51-59): *d_out = sum_{i in [i0,i1)} conj(a[i]) * b[i]. */
+int dhqr_partialdot_c64(dhqr_handle h, const void *d_a, const void *d_b, int64_t i0, int64_t i1, void *d_out,
+                        void *stream);
+
 /* ---- host-buffer entry points (single GPU): the call a CPU-side user of qr! / \ makes -------
  * hA (m x n, lda) is copied to the device, factored, and copied back with alpha; blocks until
  * the result is in host memory.  Pinned host memory makes the copies asynchronous to each other. */

@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, m, n, nb, out):
+def _worker(rank, world, port, m, n, nb, out, dup=0):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     import torch.distributed as dist
@@ -29,8 +29,16 @@ def _worker(rank, world, port, m, n, nb, out):
         c0, nl = b[rank], b[rank + 1] - b[rank]
         Al = D.colmajor_empty(m, nl, f"cuda:{rank}")
         D.fill_uniform_(Al, 0, 0, c0, h)
+        if dup:                                    # column `dup` nearly equals column dup - 30 (same column block, same panel)
+            if c0 <= dup < c0 + nl:
+                noise = D.colmajor_empty(m, 1, f"cuda:{rank}")
+                D.fill_uniform_(noise, 13, 0, 0, h)
+                Al[:, dup - c0] = Al[:, dup - 30 - c0] + 1e-11 * noise[:, 0]
+        r0 = h.get_option("wide_redone")
         Ad = D.ColumnBlockMatrix(Al, n, c0, h)
         H = D.qr_(Ad, nb=nb)
+        if dup:
+            assert h.get_option("wide_redone") == r0 + 1      # every rank learns of the refusal (the verdict travels with V)
         rhs = D.colmajor_empty(m, 1, f"cuda:{rank}")
         D.fill_uniform_(rhs, 1, 0, 0, h)
         x = D.ldiv(H, rhs[:, 0].contiguous())
@@ -45,7 +53,26 @@ def _worker(rank, world, port, m, n, nb, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [(2048, 512, 0), (1500, 333, 0), (1024, 128, 1)])
+def test_world2_restart_after_a_refused_panel(tmp_path, oracle, coracle):
+    # the third outer panel (owned by rank 1) is nearly rank deficient: the owner's wide chain refuses it on the device, the
+    # verdict reaches rank 0 with the broadcast V buffer, both ranks skip everything behind it and redo it collectively
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    m, n, dup = 2048, 512, 300
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(2, _free_port(), m, n, 0, out, dup), nprocs=2, join=True)
+    g = np.load(out)
+    A0 = coracle.fill_uniform(0, m, n)
+    A0[:, dup] = A0[:, dup - 30] + 1e-11 * coracle.fill_uniform(13, m, 1)[:, 0]
+    assert oracle.qr_residual(A0, np.asfortranarray(g["H"]), g["alphas"][0]) < 1e-13
+    assert np.array_equal(g["alphas"][0], g["alphas"][1])
+    Href = A0.copy(order="F")
+    Href, aref = coracle.qr(Href)
+    assert np.abs(g["H"][:, :256] - Href[:, :256]).max() < 1e-10      # the well-conditioned leading panels: exact parity
+
+
+@pytest.mark.parametrize("case", [(2048, 512, 0), (1500, 333, 0), (1024, 128, 1), (8192, 2048, 0)])
 def test_world2_nccl_matches_oracle(tmp_path, case, oracle, coracle):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

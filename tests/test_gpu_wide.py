@@ -97,9 +97,11 @@ def test_stage_outputs_against_the_numpy_model(D, dev, oracle, case):
     assert ok and ok2 and fo == (case == "first_order")
     sc = np.abs(R1).max()
     t2 = 1e-11 if fo else 1e-6          # the nearly dependent pair amplifies GPU-vs-numpy rounding differences by kappa ~ 3e4
-    assert np.abs(st["R1"] - R1).max() < 1e-11 * sc, "k_gemm_vta Gram / k_chol128"
+    assert np.abs(st["R1"] - R1).max() < (1e-11 if fo else 1e-5) * sc, "k_gemm_vta Gram / k_chol128"
+    G1 = P.T @ P
+    assert np.abs(st["R1"].T @ st["R1"] - G1).max() < 1e-12 * np.abs(G1).max(), "k_chol128: R1'R1 = P'P"
     assert np.abs(np.tril(st["R1"], -1)).max() == 0.0
-    assert np.abs(st["Z1"] - Z1).max() < 1e-9 * np.abs(Z1).max(), "k_chol128: inverse operand"
+    assert np.abs(st["Z1"] - W.inverse_operand(st["R1"])).max() < 1e-10 * np.abs(Z1).max(), "k_chol128: inverse operand"
     assert np.abs(st["R2"] - R2).max() < t2, "k_vpk_rmul (Z1) / Gram / k_gram2_finish or k_chol128 (second)"
     assert np.abs(st["Z2"] - Z2).max() < t2, "second pass: inverse operand"
     assert np.abs(st["Z2"] @ st["R2"] - np.eye(128)).max() < 1e-13, "second pass: Z2 is the inverse operand of R2"
