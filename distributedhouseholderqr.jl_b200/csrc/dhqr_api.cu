@@ -129,7 +129,8 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
-    int cvy_persist = 1;                                                // 128-wide gemm_cvy: persistent CTAs (the operand pipeline never drains)
+    int fuse_house = 1;                                                 // nb = 1: next reflector formed inside the apply kernel (one launch per column)
+    int cvy_persist = 2;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
     int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     int tail_cols = 0;                                                  // trailing width below which the chain is considered critical
@@ -267,7 +268,7 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         CU(cudaMalloc((void**)&c->wstamps, 32 * sizeof(long long)));
         CU(cudaMemset(c->wstamps, 0, 32 * sizeof(long long)));
     }
-    TRY(ensure(&c->v1, &c->v1_elems, (size_t)m + 4));
+    TRY(ensure(&c->v1, &c->v1_elems, (size_t)2 * rup(m + 4, 2)));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)1));
     return 0;
 }
@@ -396,8 +397,9 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     g2.ctl = c->wctl; g2.gate = gate;
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
     g2.tiles_m = (int)grid2.x; g2.tiles_n = (int)grid2.y;
-    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_persist)
-        k_gemm_cvy_p<<<std::min<int>(g2.tiles_m * g2.tiles_n, 2 * c->sms), 9 * 32, smem_g2(), st>>>(g2);
+    g2.tiles_per_cta = c->cvy_persist;
+    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_persist > 0)
+        k_gemm_cvy_p<<<(g2.tiles_m * g2.tiles_n + c->cvy_persist - 1) / c->cvy_persist, 9 * 32, smem_g2(), st>>>(g2);
     else if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_defer) K_G2D<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else K_G2<<<grid2, 5 * 32, smem_g2(), st>>>(g2);
@@ -869,6 +871,26 @@ static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, 
     TRY(check_partition(col0s, nls, n));
     TRY(ensure_workspace(c, m, nl));
     const int64_t lend = col0 + nl;
+    if (c->nranks == 1 && n > 0 && (size_t)((m + 2) & ~(int64_t)1) * 8 * (A1_CW + 1) <= 200 * 1024 && c->fuse_house) {
+        // single GPU, the column tile fits in shared memory: one launch per column step (the next reflector is formed by the
+        // CTA that has just updated its column, k_apply1_tma), two v buffers alternating between steps
+        const int64_t voff = rup(m + 4, 2);
+        k_house1<<<1, 1024, 0, st>>>(A, m, alpha, c->v1);
+        TRY(post(c, st, "k_house1"));
+        for (int64_t j = 0; j + 1 < n; ++j) {
+            const int lead = (int)(j & 1);
+            const int64_t lenw = m - j + lead, lenp = (lenw + 1) & ~(int64_t)1;
+            const int nc = (int)(n - j - 1);
+            double* C = A + (j + 1) * lda + (j - lead);
+            const int aligned = (((uintptr_t)C & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+            double* vcur = c->v1 + (j & 1) * voff, *vnext = c->v1 + ((j + 1) & 1) * voff;
+            pre(c, st);
+            k_apply1_tma<<<(nc + A1_CW - 1) / A1_CW, A1_THREADS, (size_t)lenp * 8 * (A1_CW + 1), st>>>(vcur, lenw, C, lda, nc, aligned, vnext,
+                                                                                                   alpha + j + 1, lead);
+            TRY(post(c, st, "k_apply1_tma", 16.0 * (double)(m - j) * nc));
+        }
+        return 0;
+    }
     for (int owner = 0; owner < c->nranks; ++owner) {
         for (int64_t j = col0s[owner]; j < col0s[owner] + nls[owner]; ++j) {
             const int lead = (int)(j & 1);          // window starts on an even row so TMA sources stay 16B aligned
@@ -891,7 +913,7 @@ static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, 
             const size_t smem = (size_t)lenp * 8 * (A1_CW + 1);
             if (smem <= 200 * 1024) {
                 const int aligned = (((uintptr_t)C & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
-                k_apply1_tma<<<(nc + A1_CW - 1) / A1_CW, A1_THREADS, smem, st>>>(c->v1, lenw, C, lda, nc, aligned);
+                k_apply1_tma<<<(nc + A1_CW - 1) / A1_CW, A1_THREADS, smem, st>>>(c->v1, lenw, C, lda, nc, aligned, nullptr, nullptr, lead);
                 TRY(post(c, st, "k_apply1_tma"));
             } else {
                 k_apply1_direct<<<std::min(nc, 8 * c->sms), A1_THREADS, 0, st>>>(c->v1, lenw, C, lda, nc);
@@ -1053,8 +1075,11 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "fuse_house")) {
+        c->fuse_house = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_persist")) {
-        c->cvy_persist = value ? 1 : 0;
+        if (value < 0 || value > 1 << 20) return set_err(-3, "cvy_persist out of range");
+        c->cvy_persist = (int)value;
     } else if (!strcmp(key, "cvy_defer")) {
         c->cvy_defer = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_stagger")) {

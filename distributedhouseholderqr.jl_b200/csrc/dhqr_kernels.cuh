@@ -311,6 +311,7 @@ struct GemmCvyArgs {
     const WideCtl* ctl; // speculative panel chain: skip when a panel below `gate` was refused (may be null)
     int gate;
     int tiles_m, tiles_n;   // persistent variant: row tiles (of 128) x column tiles (of 64)
+    int tiles_per_cta;      // persistent variant: consecutive tiles one CTA walks through before it retires
 };
 
 // DEFER (requires nkq == MI, i.e. the 128-wide update with 32-row warp tiles): the accumulators start at zero and the C tile is
@@ -487,10 +488,12 @@ __global__ void __launch_bounds__((WM * 2 + 1) * 32, MINB) k_gemm_cvy(GemmCvyArg
 }
 
 // ------------------------------------------------------------------------------------------------
-// gemm_cvy_p: the 128-wide update C += V Y with PERSISTENT CTAs (2 per SM, each walking over its tiles).  Same tile, same warp
+// gemm_cvy_p: the 128-wide update C += V Y with CTAs that walk through `tiles_per_cta` consecutive tiles.  Same tile, same warp
 // layout and the same deferred C reads as k_gemm_cvy<4, 2, true>; what changes is that the TMA producer warp runs ahead across
-// tile boundaries, so the operand pipeline of a CTA never drains: a one-tile CTA pays launch + barrier set-up + the first two
-// stage fills (about 4 of its 21 microseconds, profiles/r01_prof_cvy_ncu.txt) before its first DMMA.
+// tile boundaries, so the operand pipeline of a CTA does not drain between its tiles: a one-tile CTA pays launch + barrier
+// set-up + the first two stage fills (about 4 of its 21 microseconds, profiles/r01_prof_cvy_ncu.txt) before its first DMMA.
+// The walk is kept SHORT on purpose: under look-ahead the panel chain's kernels (high-priority stream) only get SMs when CTAs of
+// the bulk update retire; fully persistent CTAs starve the chain and serialise the schedule (measured: 41.5 -> 45.4 ms).
 //   tile t -> row tile t % tiles_m, column tile t / tiles_m: consecutive tiles of a CTA share the Y block (L2).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_p(GemmCvyArgs a) {
@@ -514,12 +517,13 @@ __global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_p(GemmCvyArgs a) {
     }
     __syncthreads();
     const int ntiles = a.tiles_m * a.tiles_n;
+    const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, ntiles);
 
     if (warp == NCW) {
         // ===== TMA producer warp: (tile, k-stage) pairs back to back =====
         if (lane == 0) {
             int g = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = t_lo; t < t_hi; ++t) {
                 const int bx = t % a.tiles_m, by = t / a.tiles_m;
                 const double* v0 = a.vpk + (int64_t)(2 * bx) * VPK_CHUNK + (int64_t)a.voff * LD1;
                 const double* y0 = a.ypk + (int64_t)by * a.nkq_alloc * (BN * LDK);
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_p(GemmCvyArgs a) {
     const double* v0s = sV + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
     const double* y0s = sY + wn * WTN * LDK + fragB;
     int g = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int t = t_lo; t < t_hi; ++t) {
         const int bx = t % a.tiles_m, by = t / a.tiles_m;
         const int64_t rbase = (int64_t)bx * BM + wm * WTM + (lane >> 2);
         const int cbase = by * BN + wn * WTN + (lane & 3) * 2;
@@ -1664,12 +1668,18 @@ __global__ void __launch_bounds__(1024, 1) k_house1(double* __restrict__ col, in
 
 constexpr int A1_CW = 2;         // columns per CTA
 constexpr int A1_THREADS = 256;
-// staged variant: requires (len_pad * 8 * (A1_CW + 1)) bytes of smem, 16B-aligned column starts
+// staged variant: requires (len_pad * 8 * (A1_CW + 1)) bytes of smem, 16B-aligned column starts.
+// Fused next reflector (vnext != null, single GPU): the first column of CTA 0 is column j+1; once it is updated the same CTA
+// runs S:129-135 on it (norm, alpha, scale: what k_house1 does) and leaves v_{j+1} in vnext for the next launch, so a column
+// step is ONE launch instead of two and the one-CTA k_house1 leaves the critical path.  `lead` = j & 1 (the window starts on
+// an even row); the next window starts at row j + 1 - lead_next with lead_next = 1 - lead.
 __global__ void __launch_bounds__(A1_THREADS) k_apply1_tma(const double* __restrict__ v, int64_t len,
-                                                          double* __restrict__ C, int64_t ldc, int ncols, int aligned) {
+                                                          double* __restrict__ C, int64_t ldc, int ncols, int aligned,
+                                                          double* __restrict__ vnext, double* __restrict__ alpha_next, int lead) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ double red[A1_CW][A1_THREADS / 32];
+    __shared__ double hs[2];
     const int64_t lenp = (len + 1) & ~(int64_t)1;
     double* sv = reinterpret_cast<double*>(smem_raw);
     double* sc = sv + lenp;   // [A1_CW][lenp]
@@ -1703,12 +1713,52 @@ __global__ void __launch_bounds__(A1_THREADS) k_apply1_tma(const double* __restr
         if (lane == 0) red[c][warp] = acc;
     }
     __syncthreads();
+    const bool next = vnext != nullptr && blockIdx.x == 0;
     for (int c = 0; c < nc; ++c) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < A1_THREADS / 32; ++w) s += red[c][w];
         double* out = C + (int64_t)(c0 + c) * ldc;
-        for (int64_t i = tid; i < len; i += A1_THREADS) out[i] = sc[c * lenp + i] - sv[i] * s;   // S:209 hotloop!
+        for (int64_t i = tid; i < len; i += A1_THREADS) {
+            const double x = sc[c * lenp + i] - sv[i] * s;                                   // S:209 hotloop!
+            out[i] = x;
+            if (next && c == 0) sc[i] = x;
+        }
+    }
+    if (!next) return;
+    // S:129-135 for column j+1 (rows >= j+1 = window rows >= i1)
+    const int64_t i1 = 1 + lead;
+    __syncthreads();
+    double acc = 0.0;
+    for (int64_t i = i1 + tid; i < len; i += A1_THREADS) acc += sc[i] * sc[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[0][warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < A1_THREADS / 32; ++w) t += red[0][w];
+        const double x0 = sc[i1];
+        const double sn = sqrt(t);
+        const double sg = x0 > 0.0 ? 1.0 : (x0 < 0.0 ? -1.0 : 0.0);
+        const double al = -sg * sn;
+        *alpha_next = al;
+        hs[0] = al;
+        hs[1] = 1.0 / sqrt(sn * (sn + fabs(x0)));
+    }
+    __syncthreads();
+    const double al = hs[0], f = hs[1];
+    const int leadn = 1 - lead;
+    for (int64_t i = i1 + tid; i < len; i += A1_THREADS) {
+        double x = sc[i];
+        if (i == i1) x -= al;
+        x *= f;
+        C[i] = x;                                   // column j+1 of the matrix: the reflector in place (S:133-135)
+        vnext[leadn + (i - i1)] = x;
+    }
+    if (tid == 0) {
+        if (leadn) vnext[0] = 0.0;
+        vnext[leadn + (len - i1)] = 0.0;            // pad: the staged copy moves whole 16-byte units
     }
 }
 // direct variant (column tile does not fit in shared memory): two passes, second read hits L2
