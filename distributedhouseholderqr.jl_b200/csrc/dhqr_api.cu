@@ -130,7 +130,7 @@ struct dhqr_context {
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
     int fuse_house = 1;                                                 // nb = 1: next reflector formed inside the apply kernel (one launch per column)
-    int cvy_persist = 2;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
+    int cvy_persist = 1;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
     int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
     int tail_cols = 0;                                                  // trailing width below which the chain is considered critical
@@ -885,8 +885,19 @@ static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, 
             const int aligned = (((uintptr_t)C & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
             double* vcur = c->v1 + (j & 1) * voff, *vnext = c->v1 + ((j + 1) & 1) * voff;
             pre(c, st);
-            k_apply1_tma<<<(nc + A1_CW - 1) / A1_CW, A1_THREADS, (size_t)lenp * 8 * (A1_CW + 1), st>>>(vcur, lenw, C, lda, nc, aligned, vnext,
-                                                                                                   alpha + j + 1, lead);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((nc + A1_CW - 1) / A1_CW);
+            cfg.blockDim = dim3(A1_THREADS);
+            cfg.dynamicSmemBytes = (size_t)lenp * 8 * (A1_CW + 1);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = c->profile ? 0 : 1;   // event brackets want plain stream order
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            const double* vc = vcur;
+            const int64_t ldc = lda;
+            CU(cudaLaunchKernelEx(&cfg, k_apply1_tma, vc, lenw, C, ldc, nc, aligned, vnext, alpha + j + 1, lead));
             TRY(post(c, st, "k_apply1_tma", 16.0 * (double)(m - j) * nc));
         }
         return 0;

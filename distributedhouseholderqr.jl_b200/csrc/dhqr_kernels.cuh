@@ -1691,6 +1691,10 @@ __global__ void __launch_bounds__(A1_THREADS) k_apply1_tma(const double* __restr
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
+    // Programmatic dependent launch: column step j+1 is launched while step j still runs, so that its CTAs are resident and
+    // past their prologue the moment step j's memory is complete (every byte they read was written by step j).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     // generic fill of what TMA cannot move
     for (int c = 0; c < nc; ++c)
