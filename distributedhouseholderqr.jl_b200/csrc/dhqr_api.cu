@@ -129,6 +129,10 @@ struct dhqr_context {
     int panel_fast = 1;
     unsigned int* sm_ticket = nullptr;                                  // per-SM counters for gemm_cvy phase staggering
     int cvy_stagger = 0;
+    int bs_wave = 1;                                                    // back-substitution as one wavefront launch per right-hand side
+    int bs_wave_max_ctas = 0;                                           // co-residency limit of k_backsolve_wave on this device
+    unsigned long long* bs_cells = nullptr; size_t bs_cells_blocks = 0; // x cells of the wavefront ([block][32][2 words])
+    uint32_t bs_epoch = 0;
     int fuse_house = 1;                                                 // nb = 1: next reflector formed inside the apply kernel (one launch per column)
     int cvy_persist = 1;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
@@ -563,7 +567,7 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
         return post(c, st, "k_gram128", 2.0 * (double)g.rows * WP * WP);
     };
     pre(c, st);
-    dim3 pgrid((unsigned)std::min<int64_t>((g.vrows + 255) / 256, 4 * c->sms), WP);
+    dim3 pgrid((unsigned)std::min<int64_t>((g.vrows / 4 + 255) / 256, 4 * c->sms), WP);
     k_pack<<<pgrid, 256, 0, st>>>(P, lda, g.rows, WP, 0, vpk, 0, 0, g.vrows);
     TRY(post(c, st, "k_pack"));
     TRY(gram());
@@ -951,7 +955,7 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
         const int64_t r0 = cs & ~(int64_t)31;
         const int64_t rows = m - r0, vrows = rup(rows, 128);
         const int nbp = kb <= IB ? IB : NBMAX;
-        dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbp);
+        dim3 grid((unsigned)std::min<int64_t>((vrows / 4 + 255) / 256, 4 * c->sms), nbp);
         k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk2[0], 0, cs - r0, vrows);
         TRY(post(c, st, "k_pack"));
         TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbp, rows, cs - r0, b + r0, ldb, nrhs, 0, false, nullptr, 0, notrans));
@@ -961,8 +965,22 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
 
 static int backsolve_local(dhqr_context* c, cudaStream_t st, int64_t col0, int64_t nl, const double* A, int64_t lda,
                            const double* alpha, double* y, int64_t ldy, int nrhs, double* x, int64_t ldx) {
-    // blocks of BS_BLK columns, last to first (S:260: i = n:-1:1)
     if (nl <= 0) return 0;
+    // one launch per right-hand side: a wavefront over 32-row strips (k_backsolve_wave); needs every CTA resident at once
+    const int64_t nbk = (nl + 31) / 32, nlow = (col0 + 31) / 32;
+    if (c->bs_wave && nbk + nlow <= c->bs_wave_max_ctas && nbk <= (int64_t)c->bs_cells_blocks) {
+        for (int rhs = 0; rhs < nrhs; ++rhs) {
+            if (c->bs_epoch > 0xFFFFFFF0u) {
+                CU(cudaMemsetAsync(c->bs_cells, 0, (size_t)c->bs_cells_blocks * 32 * 16, st));
+                c->bs_epoch = 0;
+            }
+            k_backsolve_wave<<<(unsigned)(nbk + nlow), BW_THREADS, 0, st>>>(A, lda, alpha, y + (int64_t)rhs * ldy, x + (int64_t)rhs * ldx, col0, nl,
+                                                                          (int)nlow, c->bs_cells, ++c->bs_epoch);
+            TRY(post(c, st, "k_backsolve_wave"));
+        }
+        return 0;
+    }
+    // fallback: blocks of BS_BLK columns, last to first (S:260: i = n:-1:1), one launch per block
     for (int64_t o = ((nl - 1) / BS_BLK) * BS_BLK; o >= 0; o -= BS_BLK) {
         const int bs = (int)std::min<int64_t>(BS_BLK, nl - o);
         const int64_t c0 = col0 + o;
@@ -1047,7 +1065,7 @@ int dhqr_destroy(dhqr_handle c) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
-    cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps);
+    cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps); cudaFree(c->bs_cells);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
@@ -1086,6 +1104,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "bs_wave")) {
+        c->bs_wave = value ? 1 : 0;
     } else if (!strcmp(key, "fuse_house")) {
         c->fuse_house = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_persist")) {
@@ -1268,6 +1288,19 @@ int dhqr_backsolve_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0,
     TRY(gather_partition(c, st, col0, n_local, col0s, nls));
     TRY(check_partition(col0s, nls, n_global));
     TRY(ensure(&c->xbuf, &c->xbuf_elems, (size_t)n_global * nrhs));
+    if (c->bs_cells_blocks < (size_t)(n_local + 31) / 32 + 1) {
+        if (c->bs_cells) CU(cudaFree(c->bs_cells));
+        c->bs_cells = nullptr;
+        c->bs_cells_blocks = (size_t)(n_local + 31) / 32 + 64;
+        CU(cudaMalloc((void**)&c->bs_cells, c->bs_cells_blocks * 32 * 16));
+        CU(cudaMemset(c->bs_cells, 0, c->bs_cells_blocks * 32 * 16));
+        c->bs_epoch = 0;
+    }
+    if (!c->bs_wave_max_ctas) {
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_backsolve_wave, BW_THREADS, 0));
+        c->bs_wave_max_ctas = std::max(1, per_sm * c->sms);
+    }
     // C4 (S:260-267), column oriented: the last owner solves its block of unknowns and removes their
     // contribution from the rows above; the partially reduced right-hand side then moves one rank down.
     const size_t cnt = (size_t)ldb * (nrhs - 1) + n_global;
@@ -1537,7 +1570,7 @@ int dhqr_k_block_reflector_f64(dhqr_handle c, int64_t rows, int nbp, const doubl
     TRY(ensure_workspace(c, rows, ncols));
     const int nbk = nbp <= IB ? IB : NBMAX;
     const int64_t vrows = rup(rows, 128);
-    dim3 grid((unsigned)std::min<int64_t>((vrows + 255) / 256, 4 * c->sms), nbk);
+    dim3 grid((unsigned)std::min<int64_t>((vrows / 4 + 255) / 256, 4 * c->sms), nbk);
     k_pack<<<grid, 256, 0, st>>>(dV, ldv, rows, nbp, 0, c->vpk2[0], 0, 0, vrows);
     TRY(post(c, st, "k_pack"));
     TRY(apply_block_reflector(c, st, c->vpk2[0], c->ws[0], 0, nbk, rows, row_lo, dC, ldc, ncols));

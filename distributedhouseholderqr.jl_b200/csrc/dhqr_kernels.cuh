@@ -1570,12 +1570,32 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pack(const double* __restrict__ A, int64_t lda, int64_t mp, int kb, int tril, double* __restrict__ vpk,
                        int voff, int64_t vtop, int64_t vrows) {
+    // four consecutive window rows per thread (they never straddle a 64-row chunk): two 16-byte stores, and two 16-byte loads
+    // when the source is aligned
     const int c = blockIdx.y;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < vrows; r += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pr = r - vtop;   // panel-relative row
-        double v = 0.0;
-        if (c < kb && pr >= (tril ? c : 0) && pr < mp) v = A[(int64_t)c * lda + pr];
-        vpk[vpk_index(r, voff + c)] = v;
+    const bool fast = ((vtop & 3) == 0) && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    for (int64_t r = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); r < vrows; r += 4 * (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pr = r - vtop;   // panel-relative row of the first of the four
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (c < kb) {
+            const double* src = A + (int64_t)c * lda + pr;
+            if (fast && pr >= 0 && pr + 3 < mp) {
+                const double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2);
+                v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (pr + q >= 0 && pr + q < mp) v[q] = src[q];
+            }
+            if (tril) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (pr + q < c) v[q] = 0.0;
+            }
+        }
+        double* dst = vpk + vpk_index(r, voff + c);
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
     }
 }
 // zero packed columns [c0, c1) over all chunks
@@ -1617,6 +1637,72 @@ __global__ void __launch_bounds__(256) k_backsolve_step(const double* __restrict
             yr[r] -= acc;
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// back-substitution as ONE launch (S:256-282, column oriented): a wavefront over 32-row strips.
+//   CTA (NLOW + k) owns the diagonal strip of local block k (rows = columns [col0 + 32k, +bs)): it keeps its piece of y in
+//   shared memory, subtracts R[strip, block b] x_b for the later blocks b = last .. k+1 as their x_b appear, then solves its own
+//   32 x 32 diagonal block (warp-shuffle substitution, diag(R) = alpha) and publishes x_k.  CTAs 0 .. NLOW-1 own the rows above
+//   this rank's columns (strips of 32 rows of [0, col0)): update only.  x_b travels in self-validating cells (value + launch
+//   tag in one 16-byte store, like the panel kernel's exchange): one L2 round trip from "solved" to "seen", no flags, no
+//   fences; the tile of R a CTA needs next is loaded BEFORE it starts polling, so the critical path per block is
+//   substitution + one L2 hand-off + a 32 x 32 matrix-vector product.  All CTAs must be co-resident (they spin): the host checks.
+// ------------------------------------------------------------------------------------------------
+constexpr int BW_THREADS = 128;
+__global__ void __launch_bounds__(BW_THREADS) k_backsolve_wave(const double* __restrict__ A, int64_t lda, const double* __restrict__ alpha,
+                                                               double* __restrict__ y, double* __restrict__ x, int64_t col0, int64_t nl,
+                                                               int nlow, unsigned long long* cells, uint32_t tag) {
+    __shared__ double sy[32], sx[32], part[4][32], sR[32][33];
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const int nbk = (int)((nl + 31) / 32);
+    const bool diag = (int)blockIdx.x >= nlow;
+    const int k = diag ? (int)blockIdx.x - nlow : -1;                       // own block (diag strips)
+    const int64_t r0 = diag ? col0 + 32 * (int64_t)k : 32 * (int64_t)blockIdx.x;   // first row of the strip
+    const int nr = (int)min((int64_t)32, (diag ? col0 + nl : col0) - r0);          // rows in the strip
+    if (tid < 32) sy[tid] = tid < nr ? y[r0 + tid] : 0.0;
+    if (diag) {                                                                // own diagonal block: triu(A_bb, 1), by columns
+        for (int e = tid; e < 32 * 32; e += BW_THREADS) {
+            const int r = e & 31, cc = e >> 5;
+            sR[r][cc] = (r < cc && cc < nr) ? A[(32 * (int64_t)k + cc) * lda + r0 + r] : 0.0;
+        }
+    }
+    __syncthreads();
+    for (int b = nbk - 1; b > k; --b) {
+        const int bs = (int)min((int64_t)32, nl - 32 * (int64_t)b);
+        // this thread's 8 entries of R[strip, block b]: row `lane`, columns 8 grp .. 8 grp + 7 (issued before the wait)
+        double rv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int cc = 8 * grp + q;
+            rv[q] = (lane < nr && cc < bs) ? A[(32 * (int64_t)b + cc) * lda + r0 + lane] : 0.0;
+        }
+        if (tid < 32) sx[tid] = tid < bs ? ll_wait(cells + ((size_t)b * 32 + tid) * 2, tag, 0) : 0.0;
+        __syncthreads();
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += rv[q] * sx[8 * grp + q];
+        part[grp][lane] = acc;
+        __syncthreads();
+        if (tid < 32) sy[tid] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+        __syncthreads();
+    }
+    if (!diag) {
+        if (tid < nr) y[r0 + tid] = sy[tid];
+        return;
+    }
+    if (tid < 32) {                                                            // x_k = R_kk^{-1} y_k (S:266-267, i = last .. first)
+        double yk = sy[lane];
+        for (int i = nr - 1; i >= 0; --i) {
+            const double xi = __shfl_sync(0xffffffffu, yk, i) / alpha[r0 + i];
+            if (lane == i) yk = xi;
+            if (lane < i) yk -= sR[lane][i] * xi;
+        }
+        if (lane < nr) {
+            ll_store(cells + ((size_t)k * 32 + lane) * 2, yk, tag);
+            x[r0 + lane] = yk;
+        }
     }
 }
 
