@@ -1464,6 +1464,10 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
         if (ns < n) {
             cudaEventCreateWithFlags(&evUp, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&evR12, cudaEventDisableTiming);
+            // the right half goes up AFTER the left half (two concurrent uploads would share the link and delay the start of
+            // the factorisation by half an upload), on its own stream so that it overlaps the factorisation of the left half
+            cudaEventRecord(evUp, st);
+            cudaStreamWaitEvent(c->h2d_stream, evUp, 0);
             if (cudaMemcpy2DAsync(dA + ns * ldd, (size_t)ldd * 8, hA + ns * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(n - ns),
                                   cudaMemcpyHostToDevice, c->h2d_stream) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
             cudaEventRecord(evUp, c->h2d_stream);
