@@ -114,11 +114,13 @@ struct dhqr_context {
         double* wsum = nullptr;  size_t wsum_elems = 0;                 // reduced Wext
         double* ypk = nullptr;   size_t ypk_elems = 0;                  // packed Y = -T'W
         double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
-    } ws[2];
+    } ws[3];                                                            // [2]: the chain's second apply (columns of panel k+2) on its own stream
     double* linv_ring[3] = {nullptr, nullptr, nullptr};               // T' of the outer panels in flight (look-ahead)
     cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
+    cudaStream_t hp2_stream = nullptr;                                  // the chain's second apply (V_k -> columns of panel k+2), high priority
+    int hp2 = 1;                                                        // option: use it (0: that apply stays on the chain's stream)
     int lookahead = 1;
     int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
     std::vector<float> la_times;                                        // [k][3]: panel k done (hp), next k signalled (st), bulk k done (st), ms since start
@@ -243,9 +245,10 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         c->vrows_cap = vrows;
     }
     const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
         auto& w = c->ws[b];
-        TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)std::max(WPART_TILES, tiles_max) * NBMAX * G1_BN));
+        // set 2 only ever updates the <= 128 columns of one panel: a quarter of the split-K partial buffer is plenty
+        TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)(b < 2 ? std::max(WPART_TILES, tiles_max) : WPART_TILES / 4) * NBMAX * G1_BN));
         TRY(ensure(&w.wsum, &w.wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
         TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
         TRY(ensure(&w.linv, &w.linv_elems, (size_t)NBMAX * NBMAX));
@@ -673,9 +676,11 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
     const int64_t lend = col0 + nl;
     const int K = (int)panels.size(), K0 = pl.kstart;
     cudaStream_t hp = c->hp_stream;
-    std::vector<cudaEvent_t> evPanel(K), evNext(K), evBulk(K);
+    std::vector<cudaEvent_t> evPanel(K), evNext(K), evBulk(K), evA2(K);
+    std::vector<char> haveA2(K, 0);
     const unsigned evflags = c->la_trace ? cudaEventDefault : cudaEventDisableTiming;
     for (int k = K0; k < K; ++k) {
+        CU(cudaEventCreateWithFlags(&evA2[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&evPanel[k], evflags));
         CU(cudaEventCreateWithFlags(&evNext[k], evflags));
         CU(cudaEventCreateWithFlags(&evBulk[k], evflags));
@@ -745,6 +750,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                 }
                 if (c->rank == panels[k + 1].owner) {
                     wait_panel(hp, k);
+                    if (k - 1 >= K0 && haveA2[k - 1]) cudaStreamWaitEvent(hp, evA2[k - 1], 0);   // V_{k-1} reached these columns
                     if (clip(t0, t1, lo, hi)) {
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
                                                         lda, (int)(hi - lo), 0, false, lk, k + 1))) break;
@@ -762,15 +768,24 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                 }
                 if ((rc = publish(k + 1))) break;
             }
-            // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1
+            // columns of panel k+2: their V_0..V_{k-1} come from the bulk updates up to k-1.  This apply is off the chain's
+            // stream (it overlaps the factorisation of panel k+1); the chain picks it up through evA2[k] before it applies
+            // V_{k+1} to the same columns.
             if (clip(t1, t2, lo, hi)) {
-                if (k - 1 >= K0) cudaStreamWaitEvent(hp, evBulk[k - 1], 0);
-                wait_panel(hp, k);
+                cudaStream_t s2 = c->hp2 ? c->hp2_stream : hp;
+                if (s2 != hp) {
+                    cudaEventRecord(evA2[k], hp);                        // (used as a scratch event first: order s2 behind hp so far,
+                    cudaStreamWaitEvent(s2, evA2[k], 0);                 //  i.e. behind T'_k and behind the last reader of workspace set 2)
+                }
+                if (k - 1 >= K0) cudaStreamWaitEvent(s2, evBulk[k - 1], 0);
+                wait_panel(s2, k);
                 const bool hadT = haveT;
-                if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
-                                                (int)(hi - lo), 0, haveT, lk, k + 1))) break;
+                if ((rc = apply_block_reflector(c, s2, vk, s2 != hp ? c->ws[2] : c->ws[1], 0, g.nbp, g.rows, p.c - g.r0,
+                                                A + (lo - col0) * lda + g.r0, lda, (int)(hi - lo), 0, haveT, lk, k + 1))) break;
                 haveT = true;
-                if (!hadT) cudaEventRecord(evNext[k], hp);               // T'_k came from this apply
+                if (!hadT) cudaEventRecord(evNext[k], s2);               // T'_k came from this apply
+                cudaEventRecord(evA2[k], s2);
+                haveA2[k] = true;
             }
             if (!haveT) cudaEventRecord(evNext[k], hp);                  // keep the event defined (timeline tracing)
             wait_panel(st, k);
@@ -805,13 +820,15 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventRecord(hpdone, cs);
         cudaStreamWaitEvent(st, hpdone, 0);
+        cudaEventRecord(hpdone, c->hp2_stream);
+        cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventDestroy(hpdone);
     }
     for (cudaEvent_t e : evHp)
         if (e) cudaEventDestroy(e);
     // events may be destroyed once recorded/waited on: the work they order is already enqueued
     if (fork) cudaEventDestroy(fork);
-    for (int k = K0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); }
+    for (int k = K0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); cudaEventDestroy(evA2[k]); }
     if (!rc) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = set_err(1000 + (int)e, "look-ahead enqueue failed: %s", cudaGetErrorString(e));
@@ -1021,6 +1038,7 @@ static int create_common(dhqr_handle* h, int device) {
         CU(cudaStreamCreateWithPriority(&c->hp_hi, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&c->hp_lo, cudaStreamNonBlocking, lo));
         CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->hp2_stream, cudaStreamNonBlocking, hi));
         c->hp_stream = c->hp_hi;
     }
     *h = c;
@@ -1062,14 +1080,16 @@ int dhqr_destroy(dhqr_handle c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->vpk2[2]);
     for (int b = 0; b < 3; ++b) cudaFree(c->linv_ring[b]);
-    for (int b = 0; b < 2; ++b) {
-        cudaFree(c->vpk2[b]); cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
+    for (int b = 0; b < 3; ++b) {
+        if (b < 2) cudaFree(c->vpk2[b]);
+        cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
     cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps); cudaFree(c->bs_cells);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->hp2_stream) cudaStreamDestroy(c->hp2_stream);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -1104,6 +1124,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "hp2")) {
+        c->hp2 = value ? 1 : 0;
     } else if (!strcmp(key, "bs_wave")) {
         c->bs_wave = value ? 1 : 0;
     } else if (!strcmp(key, "fuse_house")) {
