@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <vector>
@@ -120,6 +121,7 @@ struct dhqr_context {
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
     cudaStream_t hp2_stream = nullptr;                                  // the chain's second apply (V_k -> columns of panel k+2), high priority
+    int host_trace = 0;                                                 // option: print a stage timeline of dhqr_qr_host_f64 to stderr
     int hp2 = 1;                                                        // option: use it (0: that apply stays on the chain's stream)
     int lookahead = 1;
     int la_trace = 0;                                                   // keep timing events of the look-ahead schedule
@@ -1124,6 +1126,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "host_trace")) {
+        c->host_trace = value ? 1 : 0;
     } else if (!strcmp(key, "hp2")) {
         c->hp2 = value ? 1 : 0;
     } else if (!strcmp(key, "bs_wave")) {
@@ -1481,8 +1485,18 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     const int64_t ns = (blocked && n >= 2048 && m >= n) ? rup(n / 2, nbe) : n;
     int rc = 0;
     cudaEvent_t evUp = nullptr, evR12 = nullptr;
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto stamp = [&](const char* what, bool sync_all) {
+        if (!c->host_trace) return;
+        if (sync_all) { cudaStreamSynchronize(st); }
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        fprintf(stderr, "[dhqr host] %-34s %8.2f ms\n", what, (ts.tv_sec - ts0.tv_sec) * 1e3 + (ts.tv_nsec - ts0.tv_nsec) * 1e-6);
+    };
     do {
         if (cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)ns, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
+        stamp("left half uploaded", true);
         if (ns < n) {
             cudaEventCreateWithFlags(&evUp, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&evR12, cudaEventDisableTiming);
@@ -1498,8 +1512,10 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
         rc = dhqr_qr_f64(c, m, ns, 0, ns, dA, ldd, dal, nb, st);
         c->mirror_host = nullptr;
         if (rc) break;
+        stamp("left half factored", true);
         if (ns < n) {
             cudaStreamWaitEvent(st, evUp, 0);
+            stamp("right half uploaded", true);
             if ((rc = ensure_workspace(c, m, n))) break;
             if ((rc = apply_qt_local(c, st, m, 0, ns, dA, ldd, dA + ns * ldd, ldd, (int)(n - ns)))) break;   // right half <- Q_left' * right half
             cudaEventRecord(evR12, st);
@@ -1507,9 +1523,11 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
             if (cudaMemcpy2DAsync(hA + ns * lda, (size_t)lda * 8, dA + ns * ldd, (size_t)ldd * 8, (size_t)ns * 8, (size_t)(n - ns),
                                   cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
             c->mirror_host = hA + ns * lda + ns; c->mirror_lda = lda;
+            stamp("right half <- Q_left' (enqueued+sync)", true);
             rc = dhqr_qr_f64(c, m - ns, n - ns, 0, n - ns, dA + ns * ldd + ns, ldd, dal + ns, nb, st);
             c->mirror_host = nullptr;
             if (rc) break;
+            stamp("right part factored", true);
         }
         if (!blocked)
             if (cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
@@ -1517,6 +1535,7 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     } while (0);
     c->mirror_host = nullptr;
     cudaError_t e0 = cudaStreamSynchronize(c->h2d_stream), e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
+    stamp("everything back on the host", false);
     for (cudaEvent_t ev : c->panel_events) cudaEventDestroy(ev);
     c->panel_events.clear();
     if (evUp) cudaEventDestroy(evUp);
