@@ -270,7 +270,7 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
     if (!c->cells) { one = 0; TRY(ensure(&c->cells, &one, (size_t)IB * (PANEL_MAXG + 2) * IB * 2)); c->ll_epoch = 0; }
     if (!c->wctl) {
         CU(cudaMalloc((void**)&c->wctl, sizeof(WideCtl)));
-        const WideCtl init = {W_NOFAIL, 0, 0, 0};
+        const WideCtl init = {W_NOFAIL, 0, {0, 0}};
         CU(cudaMemcpy(c->wctl, &init, sizeof(init), cudaMemcpyHostToDevice));
         size_t o3 = 0;
         TRY(ensure(&c->wbuf, &o3, (size_t)4 * WP * WP + 3 * XL_ELEMS));
@@ -580,16 +580,13 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
     k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
     TRY(post(c, st, "k_wreduce"));
     pre(c, st);
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 0, R1, Z1, c->wctl, step, vflag, c->wide_kappa, stamps);
+    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, R1, Z1, c->wctl, step, vflag, c->wide_kappa, stamps);
     TRY(post(c, st, "k_chol128"));
     TRY(rmul(0, nq, Z1, nullptr));
     TRY(gram());
     pre(c, st);
     k_gram2_finish<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, w.wsum, R2, Z2, c->wctl, step, vflag);
     TRY(post(c, st, "k_gram2_finish"));
-    pre(c, st);     // returns at once unless the first-order second pass was refused (WideCtl::need_full)
-    k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, 1, R2, Z2, c->wctl, step, vflag, c->wide_kappa, stamps ? stamps + 8 : nullptr);
-    TRY(post(c, st, "k_chol128_2nd"));
     pre(c, st);
     k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(R2, R1, Rt, c->wctl, step);
     TRY(post(c, st, "k_trimm128"));

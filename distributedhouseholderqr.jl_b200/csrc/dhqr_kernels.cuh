@@ -37,8 +37,7 @@ constexpr int W_NOFAIL = 0x7fffffff;
 struct WideCtl {
     int fail_step;
     int status;      // guards of the panel in flight: 0 = fine
-    int need_full;   // second Cholesky pass: 1 = Q1'Q1 is too far from I for the first-order factor, run the full kernel
-    int pad;
+    int pad[2];
 };
 __device__ __forceinline__ bool wide_gate_closed(const WideCtl* ctl, int gate) {
     return ctl && *reinterpret_cast<const volatile int*>(&ctl->fail_step) < gate;

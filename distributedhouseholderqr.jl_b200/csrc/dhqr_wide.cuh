@@ -34,6 +34,7 @@ namespace dhqr {
 __host__ __device__ __forceinline__ constexpr int xl_ld(int nbk) { return 32 * (nbk + 1) + 4; }
 __host__ __device__ __forceinline__ constexpr int xl_off(int nbk) { return nbk == 0 ? 0 : (nbk == 1 ? 1152 : (nbk == 2 ? 3328 : 6528)); }
 constexpr int XL_ELEMS = 10752;    // 32 * (36 + 68 + 100 + 132)
+constexpr double FIRST_ORDER_MAX = 1e-9;   // second pass: max |Q1'Q1 - I| accepted (chol(I + E) to first order in E)
 
 __device__ __forceinline__ double rsqrt_nb(double d) {
     // rsqrt(double) without the library's slow-path branch: MUFU seed + one cubic step (the fast path of rsqrt())
@@ -56,11 +57,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ------------------------------------------------------------------------------------------------
 // chol128: R = chol(G) (upper) and its blocked inverse operand Z; one CTA of 512 threads.  G: [j * 128 + i] (k_wreduce).
-//   second == 0: guards = positive finite pivots and the conditioning estimate
-//                    est^2 = sum_b ||diag(||p_j||) Z_bb||_F^2 + sum_{a<b} ||Z_ab||_F^2 <= kappa_max^2
-//                (inverting diagonal blocks explicitly costs ~1e-17 x est in ||QR - A|| / ||A||, invariant under column
-//                scaling: tests/test_widepanel_model.py)
-//   second != 0: the fallback of k_gram2_finish (runs only when WideCtl::need_full is set): guard max |G - I| <= 1/(4*128).
+//   Guards: positive finite pivots and the conditioning estimate
+//       est^2 = sum_b ||diag(||p_j||) Z_bb||_F^2 + sum_{a<b} ||Z_ab||_F^2 <= kappa_max^2
+//   (inverting diagonal blocks explicitly costs ~1e-17 x est in ||QR - A|| / ||A||, invariant under column scaling:
+//   tests/test_widepanel_model.py).
 //   The trailing matrix lives in registers: thread (warp w, lane l) holds rows w + 16 a, columns l + 32 b.  Step j: the warp
 //   that owns row j scales it (one rsqrt) and publishes it through shared memory, one barrier, and every thread updates its
 //   8 x 4 block (the symmetric update needs row j only).  The published rows are R.
@@ -68,7 +68,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 constexpr int WT = 4 * 32 * LDD;   // scratch: four inverted diagonal blocks
 constexpr size_t SMEM_WIDE1 = ((size_t)WP * WLD + WT + 8 * WP) * 8 + 64;
 
-__global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G, int second, double* __restrict__ Rp,
+__global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G, double* __restrict__ Rp,
                                                     double* __restrict__ ZL, WideCtl* ctl, int step, double* vflag,
                                                     double kappa_max, long long* stamps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
     int* sbad = reinterpret_cast<int*>(rinv + 8 * WP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (wide_gate_closed(ctl, step) || ctl->status) return;
-    if (second && !ctl->need_full) return;
     const long long t0 = clock64();
     if (tid == 0) *sbad = 0;
     double g[8][4];
@@ -97,8 +96,7 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int i = warp + 16 * a, k = lane + 32 * b;
-                if (second) bad |= !(fabs(g[a][b] - (i == k ? 1.0 : 0.0)) <= 0.25 / WP);
-                else bad |= !(fabs(g[a][b]) < 1e300);
+                bad |= !(fabs(g[a][b]) < 1e300);
                 if (i == k) dn[i] = sqrt(g[a][b]);
             }
         if (bad) *sbad = 1;
@@ -176,17 +174,15 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
             ZL[xl_off(b) + c * xl_ld(b) + 32 * a + i] = v;
             acc += v * v;
         }
-        if (!second) {
-            acc = warp_sum(acc);
-            if (lane == 0) red[warp] = acc;
-            __syncthreads();
-            if (tid == 0) {
-                double tsum = 0.0;
-                for (int w = 0; w < 16; ++w) tsum += red[w];
-                if (!(tsum <= kappa_max * kappa_max)) *sbad = 1;
-            }
-            __syncthreads();
+        acc = warp_sum(acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tsum = 0.0;
+            for (int w = 0; w < 16; ++w) tsum += red[w];
+            if (!(tsum <= kappa_max * kappa_max)) *sbad = 1;
         }
+        __syncthreads();
     }
     if (*sbad && tid == 0) {
         ctl->status = 1;
@@ -200,7 +196,9 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
 // gram2_finish: the split-K reduction of the second Gram matrix (as k_wreduce, fixed order) fused with the second Cholesky
 // pass in its first-order form.  E = G2 - I is the loss of orthogonality of the first pass; with U = striu(E) + diag(E)/2,
 // chol(I + E) = I + U + O(E^2) and its inverse is I - U + O(E^2).  max|E| <= 1e-9 bounds the neglected terms by
-// 128 * 1e-18, far below rounding; larger E sets WideCtl::need_full and k_chol128(second) redoes the pass.
+// 128 * 1e-18, far below rounding.  E is O(eps kappa^2): a panel that passed the conditioning guard of the first pass
+// (kappa <~ 1e3) sits orders of magnitude below the bound; anything larger REFUSES the panel (the driver redoes it with the
+// 32-column chain), so the chain carries no second full Cholesky.
 // One element per thread (grid 64 x 256).  Outputs: Ws (G2), Rp = R2 plain, ZL = its blocked inverse operand.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gram2_finish(const double* __restrict__ Wp, int64_t pstride, int nsplit, double* __restrict__ Ws,
@@ -222,12 +220,11 @@ __global__ void __launch_bounds__(256) k_gram2_finish(const double* __restrict__
     Ws[e] = g;
     const int i = e & (WP - 1), j = e >> 7;              // row, column
     const double E = g - (i == j ? 1.0 : 0.0);
-    if (!(fabs(E) <= 0.25 / WP)) {
+    if (!(fabs(E) <= FIRST_ORDER_MAX)) {              // also catches NaN / Inf
         ctl->status = 1;
         atomicMin(&ctl->fail_step, step);
         if (vflag) *vflag = 1.0;
     }
-    if (!(fabs(E) <= 1e-9)) ctl->need_full = 1;
     const double u = i == j ? 0.5 * E : E;
     Rp[e] = i < j ? u : (i == j ? 1.0 + u : 0.0);
     const int nbk = j >> 5;
@@ -549,7 +546,6 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
 __global__ void k_wide_begin(WideCtl* ctl, double* vflag) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->status = 0;
-        ctl->need_full = 0;
         *vflag = 0.0;
     }
 }
@@ -557,7 +553,6 @@ __global__ void k_wide_reset(WideCtl* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->fail_step = W_NOFAIL;
         ctl->status = 0;
-        ctl->need_full = 0;
     }
 }
 // after a V buffer arrived from another rank: take over the owner's verdict on the panel

@@ -2,8 +2,8 @@
 distributedhouseholderqr.jl_b200/csrc/dhqr_wide.cuh), stage by stage:
 
     G1 = P'P          R1 = chol(G1)     Z1 = blocked inverse operand of R1                Q1 = P R1^{-1} (through Z1)
-    G2 = Q1'Q1        E = G2 - I        R2 = I + U, Z2 = I - U with U = striu(E) + diag(E)/2 when max|E| <= 1e-9
-                                        (first order in E; otherwise R2 = chol(G2) like the first pass)
+    G2 = Q1'Q1        E = G2 - I        R2 = I + U, Z2 = I - U with U = striu(E) + diag(E)/2   (first order in E; a panel
+                                        with max|E| > 1e-9 is refused: it did not pass the first pass well conditioned)
     Wt = Q1[:nb] R2^{-1}   signed LU of Wt (Householder reconstruction: Ballard, Demmel, Grigori, Jacquelin, Nguyen, Solomonik 2014)
     Rr = diag(sqrt(Ud)) (I + diag(cl) striu(U))      V[nb:] = Q1[nb:] (Rr R2)^{-1}      Rt = R2 R1
 
@@ -19,7 +19,6 @@ reference's column recurrences and that the guards refuse ill-conditioned panels
 import numpy as np
 
 NB = 128
-ORTH_MAX = 0.25          # guard on ||Q1'Q1 - I||: max-norm <= ORTH_MAX / nb  =>  2-norm <= 1/4
 KAPPA_MAX = 1.0e3        # guard on ||D R1^{-1}||_F, D = diag(||p_j||): multiplying by the EXPLICIT inverse (a GEMM on the tensor
                          # pipe instead of a substitution) costs ~1e-17 x that number in ||QR - A|| / ||A|| (measured below)
 
@@ -125,21 +124,20 @@ def signed_lu(W):
 
 
 def second_pass(G2):
-    """(R2, Z2, ok, first_order) from G2 = Q1'Q1: guard, then the first-order factor or a full Cholesky (k_gram2_finish)."""
+    """(R2, Z2, ok) from G2 = Q1'Q1 (k_gram2_finish): chol(I + E) and its inverse to first order in E = G2 - I; refuses the
+    panel when max|E| > FIRST_ORDER_MAX (the neglected terms are O(n E^2)) — E is O(eps kappa^2), so a panel that passed the
+    conditioning guard of the first pass is orders of magnitude below the bound."""
     n = G2.shape[0]
     E = G2 - np.eye(n)
-    if not np.all(np.abs(E) <= ORTH_MAX / n):
-        return None, None, False, False
-    if np.all(np.abs(E) <= FIRST_ORDER_MAX):
-        U = np.triu(E, 1) + np.diag(np.diag(E)) / 2
-        return np.eye(n) + U, np.eye(n) - U, True, True
-    R2, ok = cholesky_upper(G2)
-    return R2, (inverse_operand(R2) if ok else None), ok, False
+    if not np.all(np.abs(E) <= FIRST_ORDER_MAX):
+        return None, None, False
+    U = np.triu(E, 1) + np.diag(np.diag(E)) / 2
+    return np.eye(n) + U, np.eye(n) - U, True
 
 
 def wide_panel(P, kappa_max=KAPPA_MAX):
     """Returns (H, alpha, ok): H in the reference's storage; ok False when a guard refuses the panel (non-positive or
-    non-finite Cholesky pivot, conditioning estimate > kappa_max, or the first pass left ||Q1'Q1 - I|| > 1/4) — the driver then
+    non-finite Cholesky pivot, conditioning estimate > kappa_max, or the first pass left max|Q1'Q1 - I| > 1e-9) — the driver then
     redoes the panel with the 32-column chain.  The guards are invariant under column scaling."""
     P = np.array(P, dtype=np.float64)
     m, n = P.shape
@@ -151,7 +149,7 @@ def wide_panel(P, kappa_max=KAPPA_MAX):
     if not (kappa_estimate(R1, Z1) <= kappa_max):
         return None, None, False
     Q1 = solve_right(P, Z1)
-    R2, Z2, ok, _ = second_pass(Q1.T @ Q1)
+    R2, Z2, ok = second_pass(Q1.T @ Q1)
     if not ok:
         return None, None, False
     Rt = np.triu(R2 @ R1)                                   # k_trimm128
