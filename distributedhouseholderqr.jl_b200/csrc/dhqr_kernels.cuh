@@ -22,7 +22,6 @@ constexpr int PANEL_THREADS = 512;
 #ifndef DHQR_PANEL_VARIANT
 #define DHQR_PANEL_VARIANT 4   // bit 2: triangular solves of the panel fast path on the fp64 tensor pipe (0: row-by-row
 #endif                         // substitution on the vector pipe); A/B results in profiles/r01_panel_variants.txt.
-                               // bit 3: strip-blocked Cholesky (next-round candidate, never run on a GPU yet)
 constexpr int PANEL_VARIANT = DHQR_PANEL_VARIANT;
 // Fast-path guard on the first Cholesky factor: min / max of its diagonal.  Row-by-row substitution is backward stable for
 // any factor the other guards accept (1e-5); the blocked solves invert 8x8 diagonal blocks explicitly, which costs
@@ -1144,52 +1143,6 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
             }
             __syncthreads();
         };
-        // [PANEL_VARIANT bit 3, not built by default, not yet run on a GPU: index logic checked against a lane-level numpy
-        // emulation only]  The same factor by 8-row strips: the strip is eliminated in registers (8 dependent steps, every lane
-        // carries its column so the whole row panel R(kb:kb+8, :) falls out without a separate triangular solve), the trailing
-        // block is updated on the tensor pipe (G22 -= R12' R12, upper 8x8 tiles, operands from Rout), and the loop over the 4
-        // strips is rolled: ~10x less code than the 32 unrolled steps above and 8 instead of 32 serial steps per strip.
-        auto chol_blocked = [&](double* Rout) {
-            if (warp == 0) {
-#pragma unroll 1
-                for (int kb = 0; kb < IB; kb += 8) {
-                    double g[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g[i] = Gm[(kb + i) * LDG + lane];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const double d = __shfl_sync(0xffffffffu, g[j], kb + j);
-                        const double ri = rsqrt_nb(d);
-                        if (lane == 0) {
-                            if (!(d > 0.0) || !(d < 1e300)) bad = 1;
-                            rinv[kb + j] = ri;
-                        }
-                        const double r = lane == kb + j ? d * ri : g[j] * ri;   // R(kb + j, lane)
-                        Rout[(kb + j) * IB + lane] = lane >= kb + j ? r : 0.0;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i) {
-                            const double rji = __shfl_sync(0xffffffffu, r, kb + i);
-                            g[i] -= rji * r;
-                        }
-                    }
-                    __syncwarp();
-                    for (int I0 = kb + 8; I0 < IB; I0 += 8)
-                        for (int J0 = I0; J0 < IB; J0 += 8) {
-                            double* pc = Gm + (I0 + (lane >> 2)) * LDG + J0 + 2 * (lane & 3);
-                            double c0 = pc[0], c1 = pc[1];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const double* rr = Rout + (kb + 4 * h + (lane & 3)) * IB + (lane >> 2);
-                                dmma(c0, c1, -rr[I0], rr[J0]);
-                            }
-                            pc[0] = c0;
-                            pc[1] = c1;
-                        }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        };
         // Triangular solve on the fp64 tensor pipe: slab rows [8 tile_lo, nr) <- rows * Rm^{-1}, Rm upper triangular ([IB][IB]),
         // dgi = 1 / diag(Rm).  Blocked by 8 columns: X'_b = X_b inv(R_bb) - sum_{a<b} X'_a (R_ab inv(R_bb)); the 8x8 diagonal
         // inverses and the 6 products are formed once per call (Dv, Wn), the B fragments live in registers, and one warp
@@ -1283,7 +1236,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
         auto stamp = [&](int k) { if (ftr && tid == 0) ftr[k] = clock64() - ft0; };
         gram_exchange(0, ftag);
         stamp(1);
-        if (PANEL_VARIANT & 8) chol_blocked(R1); else chol(R1);
+        chol(R1);
         stamp(2);
         if (tid == 0 && !bad) {   // conditioning guard on the first factor
             double dmin = R1[0], dmax = R1[0];
@@ -1303,7 +1256,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(PanelArgs a) {
                 if (!(fabs(Gm[i * LDG + j] - (i == j ? 1.0 : 0.0)) <= 0.25 / IB)) bad = 1;   // max-norm test, scaled for the 2-norm
             }
             __syncthreads();
-            if (!bad) { if (PANEL_VARIANT & 8) chol_blocked(R2); else chol(R2); }
+            if (!bad) chol(R2);
             stamp(5);
         }
         __syncthreads();
