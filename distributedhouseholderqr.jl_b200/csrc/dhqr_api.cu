@@ -121,6 +121,7 @@ struct dhqr_context {
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
     cudaStream_t hp2_stream = nullptr;                                  // the chain's second apply (V_k -> columns of panel k+2), high priority
+    int wide_trecon = 1;                                                // option: T' of a wide panel from the reconstruction (k_trecon)
     int host_trace = 0;                                                 // option: print a stage timeline of dhqr_qr_host_f64 to stderr
     int hp2 = 1;                                                        // option: use it (0: that apply stays on the chain's stream)
     int lookahead = 1;
@@ -220,6 +221,7 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(k_vpk_rmul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_RMUL));
     CU(cudaFuncSetAttribute(k_trimm128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIMM));
     CU(cudaFuncSetAttribute(k_trimm_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIMM));
+    CU(cudaFuncSetAttribute(k_trecon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRECON));
     CU(cudaFuncSetAttribute(k_apply1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->attrs_set = true;
     return 0;
@@ -273,7 +275,7 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         const WideCtl init = {W_NOFAIL, 0, {0, 0}};
         CU(cudaMemcpy(c->wctl, &init, sizeof(init), cudaMemcpyHostToDevice));
         size_t o3 = 0;
-        TRY(ensure(&c->wbuf, &o3, (size_t)4 * WP * WP + 3 * XL_ELEMS));
+        TRY(ensure(&c->wbuf, &o3, (size_t)5 * WP * WP + 3 * XL_ELEMS));
         CU(cudaMalloc((void**)&c->wstamps, 32 * sizeof(long long)));
         CU(cudaMemset(c->wstamps, 0, 32 * sizeof(long long)));
     }
@@ -541,11 +543,11 @@ static bool wide_eligible(const dhqr_context* c, const Panel& p, int64_t m, int 
     return c->wide_panel && nb == WP && p.kb == WP && (p.c & 31) == 0 && m - p.c >= WP;
 }
 static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
-                                   int64_t col0, double* A, int64_t lda, double* alpha, int step) {
+                                   int64_t col0, double* A, int64_t lda, double* alpha, int step, double* linv_out) {
     const PanelGeom g = panel_geom(p, m);       // r0 == p.c: the window starts at the pivot row
     double* P = A + (p.c - col0) * lda + p.c;
-    double* R1 = c->wbuf, *R2 = R1 + WP * WP, *Rt = R2 + WP * WP, *Rr = Rt + WP * WP;
-    double* Z1 = Rr + WP * WP, *Z2 = Z1 + XL_ELEMS, *Z23 = Z2 + XL_ELEMS;
+    double* R1 = c->wbuf, *R2 = R1 + WP * WP, *Rt = R2 + WP * WP, *Rr = Rt + WP * WP, *MT = Rr + WP * WP;
+    double* Z1 = MT + WP * WP, *Z2 = Z1 + XL_ELEMS, *Z23 = Z2 + XL_ELEMS;
     double* vflag = vpk + KC1;                  // padding row 64 of packed column 0: travels with the V buffer
     const int nq = (int)(g.vrows / KC1);
     long long* stamps = c->wide_trace ? c->wstamps : nullptr;
@@ -592,8 +594,13 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
     TRY(post(c, st, "k_trimm128"));
     TRY(rmul(0, 2, Z2, nullptr));
     pre(c, st);
-    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Rr, c->wctl, step, stamps ? stamps + 16 : nullptr);
+    k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Rr, MT, c->wctl, step, stamps ? stamps + 16 : nullptr);
     TRY(post(c, st, "k_hr128"));
+    if (linv_out) {     // T' of the panel from the reconstruction: the owner's next block update needs neither V'V nor k_tinv
+        pre(c, st);
+        k_trecon<<<4, 256, SMEM_TRECON, st>>>(vpk, MT, linv_out, c->wctl, step);
+        TRY(post(c, st, "k_trecon"));
+    }
     pre(c, st);
     k_trimm_z<<<10, 256, SMEM_TRIMM, st>>>(Rr, R2, Z23, c->wctl, step);
     TRY(post(c, st, "k_trimm_z"));
@@ -603,12 +610,12 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
 }
 
 static int factor_outer_panel(dhqr_context* c, cudaStream_t st, double* vpk, dhqr_context::WSet& w, const Panel& p, int64_t m,
-                              int64_t col0, double* A, int64_t lda, double* alpha, int step, bool wide) {
+                              int64_t col0, double* A, int64_t lda, double* alpha, int step, bool wide, double* linv_out = nullptr) {
     if (c->wctl) {   // clear the guards of the previous panel and the verdict that travels with this V buffer
         k_wide_begin<<<1, 32, 0, st>>>(c->wctl, vpk + KC1);
         TRY(post(c, st, "k_wide_begin"));
     }
-    if (wide) return factor_outer_panel_wide(c, st, vpk, w, p, m, col0, A, lda, alpha, step);
+    if (wide) return factor_outer_panel_wide(c, st, vpk, w, p, m, col0, A, lda, alpha, step, c->wide_trecon ? linv_out : nullptr);
     return factor_outer_panel_narrow(c, st, vpk, w, p, m, col0, A, lda, alpha, step);
 }
 
@@ -640,9 +647,12 @@ static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_
     for (int k = pl.kstart; k < (int)panels.size(); ++k) {
         const Panel& p = panels[k];
         const PanelGeom g = panel_geom(p, m);
+        bool haveT = false;
         if (c->rank == p.owner) {
-            TRY(factor_outer_panel(c, st, vpk, w, p, m, col0, A, lda, alpha, k, plan_wide(c, pl, panels, k, m)));
+            const bool wide = plan_wide(c, pl, panels, k, m);
+            TRY(factor_outer_panel(c, st, vpk, w, p, m, col0, A, lda, alpha, k, wide, w.linv));
             TRY(mirror_panel_to_host(c, st, p, m, col0, A, lda));
+            haveT = wide && c->wide_trecon;
         }
         if (c->nranks > 1) {
             // C2 (S:141-143): the owner's reflectors go to every rank, once per panel instead of once per column
@@ -655,7 +665,7 @@ static int qr_blocked_serial(dhqr_context* c, cudaStream_t st, int64_t m, int64_
         const int64_t t0 = std::max(p.c + p.kb, col0);
         if (t0 < lend)
             TRY(apply_block_reflector(c, st, vpk, w, 0, g.nbp, g.rows, p.c - g.r0, A + (t0 - col0) * lda + g.r0, lda, (int)(lend - t0), 0,
-                                      false, nullptr, k + 1));
+                                      haveT, nullptr, k + 1));
     }
     return 0;
 }
@@ -724,9 +734,12 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         if (cudaEventCreateWithFlags(&fork, evflags) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
         cudaEventRecord(fork, st);
         cudaStreamWaitEvent(hp, fork, 0);                          // hp starts after everything already queued on st
+        std::vector<char> ownT(K, 0);       // T'_k already sits in the ring slot on this rank (wide panel factored here, k_trecon)
         if (c->rank == panels[K0].owner) {
-            if ((rc = factor_outer_panel(c, hp, c->vpk2[K0 % 3], c->ws[1], panels[K0], m, col0, A, lda, alpha, K0, plan_wide(c, pl, panels, K0, m)))) break;
+            const bool wide = plan_wide(c, pl, panels, K0, m);
+            if ((rc = factor_outer_panel(c, hp, c->vpk2[K0 % 3], c->ws[1], panels[K0], m, col0, A, lda, alpha, K0, wide, c->linv_ring[K0 % 3]))) break;
             if ((rc = mirror_panel_to_host(c, hp, panels[K0], m, col0, A, lda))) break;
+            if (wide && c->wide_trecon) { ownT[K0] = 1; cudaEventRecord(evNext[K0], hp); }
         }
         if ((rc = publish(K0))) break;
         for (int k = K0; k < K && !rc; ++k) {
@@ -739,30 +752,34 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             int64_t lo, hi;
             c->bulk_wide = (c->tail_cols <= 0) || (lend - t1 >= c->tail_cols);   // bulk-bound (wide) vs chain-bound (narrow) phase
             double* lk = c->linv_ring[k % 3];
-            bool haveT = false;                                          // T'_k in lk (this rank)
+            bool haveT = ownT[k];                                        // T'_k in lk (this rank)
             if (k + 1 < K) {
                 // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2 (and, on the owner of panel k-2,
                 // by its broadcast)
                 if (k - 2 >= K0) {
                     cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
+                    if (haveA2[k - 2]) cudaStreamWaitEvent(hp, evA2[k - 2], 0);
                     if (c->nranks > 1) cudaStreamWaitEvent(hp, evPanel[k - 2], 0);
                 }
                 if (c->rank == panels[k + 1].owner) {
                     wait_panel(hp, k);
                     if (k - 1 >= K0 && haveA2[k - 1]) cudaStreamWaitEvent(hp, evA2[k - 1], 0);   // V_{k-1} reached these columns
                     if (clip(t0, t1, lo, hi)) {
+                        const bool hadT = haveT;
                         if ((rc = apply_block_reflector(c, hp, vk, c->ws[1], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0,
-                                                        lda, (int)(hi - lo), 0, false, lk, k + 1))) break;
+                                                        lda, (int)(hi - lo), 0, haveT, lk, k + 1))) break;
                         haveT = true;
-                        cudaEventRecord(evNext[k], hp);                  // T'_k is in the ring: the bulk update may start
+                        if (!hadT) cudaEventRecord(evNext[k], hp);       // T'_k is in the ring: the bulk update may start
                     }
                     // while the bulk update is wide the panel kernel leaves most SMs to it (64 CTAs); once the trailing
                     // matrix is narrow the chain is the critical path and the panel takes every SM
                     c->panel_ctas_hint = c->bulk_wide ? c->wide_panel_ctas : (c->tail_cols > 0 ? c->sms : c->wide_panel_ctas);
-                    rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha, k + 1,
-                                            plan_wide(c, pl, panels, k + 1, m));
+                    const bool widen = plan_wide(c, pl, panels, k + 1, m);
+                    rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha, k + 1, widen,
+                                            c->linv_ring[(k + 1) % 3]);
                     c->panel_ctas_hint = 0;
                     if (rc) break;
+                    if (widen && c->wide_trecon) { ownT[k + 1] = 1; cudaEventRecord(evNext[k + 1], hp); }
                     if ((rc = mirror_panel_to_host(c, hp, panels[k + 1], m, col0, A, lda))) break;
                 }
                 if ((rc = publish(k + 1))) break;
@@ -1123,6 +1140,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "wide_trecon")) {
+        c->wide_trecon = value ? 1 : 0;
     } else if (!strcmp(key, "host_trace")) {
         c->host_trace = value ? 1 : 0;
     } else if (!strcmp(key, "hp2")) {
@@ -1638,7 +1657,7 @@ int dhqr_debug_copy_f64(dhqr_handle c, const char* which, double* d_dst, int64_t
     else if (!strcmp(which, "linv")) { src = c->ws[0].linv; have = (size_t)NBMAX * NBMAX; }
     else if (!strcmp(which, "vpk")) { src = c->vpk2[0]; have = c->vpk_elems[0]; }
     else if (!strcmp(which, "wstamps")) { src = (const double*)c->wstamps; have = c->wstamps ? 32 : 0; }
-    else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)4 * WP * WP + 3 * XL_ELEMS : 0; }
+    else if (!strcmp(which, "wide")) { src = c->wbuf; have = c->wbuf ? (size_t)5 * WP * WP + 3 * XL_ELEMS : 0; }
     else if (!strcmp(which, "panel_trace")) { src = (const double*)c->panel_trace; have = c->panel_trace ? (size_t)PANEL_MAXG * IB * 8 : 0; }
     else return set_err(-2, "unknown buffer '%s'", which);
     if (nelems < 0 || (size_t)nelems > have) return set_err(-4, "nelems out of range (have %zu)", have);
@@ -1672,7 +1691,7 @@ int dhqr_k_wide_panel_f64(dhqr_handle c, int64_t rows, double* dP, int64_t ldp, 
     k_wide_reset<<<1, 32, 0, st>>>(c->wctl);
     TRY(post(c, st, "k_wide_reset"));
     const Panel p = {0, 0, WP};
-    TRY(factor_outer_panel(c, st, c->vpk2[0], c->ws[0], p, rows, 0, dP, ldp, d_alpha, 0, true));
+    TRY(factor_outer_panel(c, st, c->vpk2[0], c->ws[0], p, rows, 0, dP, ldp, d_alpha, 0, true, c->ws[0].linv));
     WideCtl host;
     CU(cudaMemcpyAsync(&host, c->wctl, sizeof(host), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

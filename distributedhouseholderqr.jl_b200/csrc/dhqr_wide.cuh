@@ -456,12 +456,14 @@ __global__ void __launch_bounds__(256, 1) k_vpk_rmul(RmulArgs a) {
 //   S_j = -sign(w_jj), U_jj = 1 + |w_jj|, W(i,k) += (S_j / U_jj) W(i,j) W(j,k).  In the reference's storage (S:127-135):
 //   v_ij = W_ij^(j) / sqrt(U_jj) (i > j), v_jj = -S_j sqrt(U_jj), alpha_j = S_j Rt_jj, R_ij = S_i Rt_ij (i < j).
 //   The rows below the top block are V = Q Rr^{-1}, Rr = diag(sqrt(U)) (I + diag(-S/U) striu(W)), left in Rrp (plain).
+//   MTp = U_lu' D'^{-1} (lower triangular, plain) with U_lu the upper factor of the LU of E - Q S and D' = diag(v_jj): the
+//   right-hand side from which k_trecon gets the compact-WY factor, T' = V1^{-1} MT.
 //   Like k_chol128 the matrix lives in registers (rows w + 16 a, columns l + 32 b per thread); a step publishes column j and
 //   row j through double-buffered shared memory: one barrier per step.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, const double* __restrict__ Rt, double* __restrict__ P,
                                                   int64_t ldp, double* __restrict__ alpha, double* __restrict__ Rrp,
-                                                  const WideCtl* ctl, int step, long long* stamps) {
+                                                  double* __restrict__ MTp, const WideCtl* ctl, int step, long long* stamps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Wt = reinterpret_cast<double*>(smem_raw);   // [128][WLD] row-major
     double* T = Wt + WP * WLD;
@@ -530,16 +532,101 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
     for (int e = tid; e < WP * WP; e += 512) {
         const int i = e & (WP - 1), j = e >> 7;
         const double wij = Wt[i * WLD + j];
-        double v, rr;
-        if (i > j) { v = wij * rsq[j]; rr = 0.0; }
-        else if (i == j) { v = -Sg[j] * (Ud[j] * rsq[j]); rr = Ud[i] * rsq[i]; }
-        else { v = Sg[i] * Rt[e]; rr = (-Sg[i] / Ud[i]) * wij * (Ud[i] * rsq[i]); }
+        double v, rr, mt;
+        if (i > j) {
+            v = wij * rsq[j];
+            rr = 0.0;
+            mt = Wt[j * WLD + i] * Sg[i] * Sg[j] * rsq[j];       // frozen row j, column i: U_lu(j, i) / D'_j
+        } else if (i == j) {
+            v = mt = -Sg[j] * (Ud[j] * rsq[j]);
+            rr = Ud[i] * rsq[i];
+        } else {
+            v = Sg[i] * Rt[e];
+            rr = (-Sg[i] / Ud[i]) * wij * (Ud[i] * rsq[i]);
+            mt = 0.0;
+        }
         P[(int64_t)j * ldp + i] = v;
         vpk[vpk_index(i, j)] = i >= j ? v : 0.0;
         Rrp[e] = rr;
+        MTp[e] = mt;
         if (i == j) alpha[j] = Sg[j] * Rt[e];
     }
     if (stamps && tid == 0) stamps[6] = clock64() - t0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trecon: the compact-WY factor of the panel from the reconstruction itself.  I - V T V' restricted to the top block reads
+// V1 T V1' = E - Q S = L_lu U_lu, hence T' = V1^{-1} (U_lu' D'^{-1}) = V1^{-1} MT (V1 = top 128 x 128 block of V, lower
+// triangular; MT from k_hr128): a triangular solve with 128 right-hand sides instead of the 128 x 128 Gram matrix V'V over all
+// rows (2 rows 128^2 flop inside k_gemm_vta) + k_tinv on the chain.  Block column jb of T' per CTA:
+//   T'(ib, jb) = inv(V1_ii) (MT(ib, jb) - sum_{pb = jb}^{ib-1} V1(ib, pb) T'(pb, jb)),   ib = jb .. 3.
+// Output: Linv[j * 128 + i] = T'(i, j) (what k_ymake reads).  Verified against (I + stril(V'V))^{-1} to 2e-16 in numpy.
+// ------------------------------------------------------------------------------------------------
+constexpr size_t SMEM_TRECON = (size_t)(10 + 4 + 1 + 4) * 32 * 33 * 8;
+
+__global__ void __launch_bounds__(256) k_trecon(const double* __restrict__ vpk, const double* __restrict__ MTp, double* __restrict__ Linv,
+                                                const WideCtl* ctl, int step) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [10][32][33]: V1(ib, pb), pb <= ib, block index ib (ib + 1) / 2 + pb
+    double* sT = sV + 10 * 32 * 33;                      // [4][32][33]: T'(ib, jb)
+    double* sA = sT + 4 * 32 * 33;                       // [32][33]: right-hand side of the current step
+    double* sD = sA + 32 * 33;                           // [4][32][LDD]: inv(V1_ii')  (upper; element (c, r) = inv(V1_ii)(r, c))
+    if (wide_gate_closed(ctl, step) || ctl->status) return;
+    const int jb = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = lane, jq = warp;
+    for (int ib = jb; ib < 4; ++ib)
+        for (int pb = jb; pb <= ib; ++pb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cc = jq + 8 * q;
+                sV[((ib * (ib + 1) / 2 + pb) * 32 + i) * 33 + cc] = vpk[vpk_index(32 * ib + i, 32 * pb + cc)];
+            }
+    __syncthreads();
+    if (warp < 4 - jb) {                                  // inv(V1_ii) for ii = jb + warp: invert the transpose (upper) by one warp
+        const int ii = jb + warp;
+        double* U = sT + warp * 32 * 33;                  // scratch: sT is not live yet
+        const double* Vd = sV + ((ii * (ii + 1) / 2 + ii) * 32) * 33;
+        for (int r = 0; r < 32; ++r) U[lane * 33 + r] = r >= lane ? Vd[r * 33 + lane] : 0.0;     // U(c = lane, r) = V1_ii(r, c)
+        __syncwarp();
+        triu_inv32_warp(U, 33, nullptr, sD + ii * 32 * LDD, lane);
+    }
+    __syncthreads();
+    for (int ib = jb; ib < 4; ++ib) {
+        double acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = MTp[(size_t)(32 * jb + jq + 8 * q) * WP + 32 * ib + i];
+        for (int pb = jb; pb < ib; ++pb) {
+            const double* a = sV + ((ib * (ib + 1) / 2 + pb) * 32 + i) * 33;
+            const double* t = sT + pb * 32 * 33 + jq;
+#pragma unroll 8
+            for (int p = 0; p < 32; ++p) {
+                const double av = a[p];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] -= av * t[p * 33 + 8 * q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sA[i * 33 + jq + 8 * q] = acc[q];
+        __syncthreads();
+        const double* d = sD + ib * 32 * LDD;             // inv(V1_ii)(i, p) = d[p * LDD + i], p <= i
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int p = 0; p <= i; ++p) {
+            const double dv = d[p * LDD + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] += dv * sA[p * 33 + jq + 8 * q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = jq + 8 * q;
+            sT[ib * 32 * 33 + i * 33 + cc] = out[q];
+            Linv[(size_t)(32 * jb + cc) * WP + 32 * ib + i] = out[q];
+        }
+        __syncthreads();
+    }
+    // blocks above the diagonal of T' are zero (k_ymake only reads the lower triangle, tools read the whole matrix)
+    for (int ib = 0; ib < jb; ++ib)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Linv[(size_t)(32 * jb + jq + 8 * q) * WP + 32 * ib + i] = 0.0;
 }
 
 // start of a wide panel: clear the guards of the previous one and the validity flag that travels with the V buffer

@@ -63,15 +63,19 @@ def unpack_operand(zl):
 
 
 def stages(D, dev):
-    """R1, R2, Rt, Rr (plain 128 x 128, column-major) and the inverse operands Z1, Z2, Z23 left by the last wide panel."""
+    """R1, R2, Rt, Rr, MT (plain 128 x 128, column-major), the inverse operands Z1, Z2, Z23 and T' left by the last wide panel."""
     h = D.default_handle(0)
-    buf = torch.zeros(4 * 128 * 128 + 3 * XL_ELEMS, dtype=torch.float64, device=dev)
+    buf = torch.zeros(5 * 128 * 128 + 3 * XL_ELEMS, dtype=torch.float64, device=dev)
     D._lib.call("dhqr_debug_copy_f64", h.raw, b"wide", vp(buf), buf.numel(), sp())
     torch.cuda.synchronize()
     a = buf.cpu().numpy()
-    out = {k: a[i * 16384:(i + 1) * 16384].reshape(128, 128).T.copy() for i, k in enumerate(["R1", "R2", "Rt", "Rr"])}
+    out = {k: a[i * 16384:(i + 1) * 16384].reshape(128, 128).T.copy() for i, k in enumerate(["R1", "R2", "Rt", "Rr", "MT"])}
     for i, k in enumerate(["Z1", "Z2", "Z23"]):
-        out[k] = unpack_operand(a[4 * 16384 + i * XL_ELEMS:4 * 16384 + (i + 1) * XL_ELEMS])
+        out[k] = unpack_operand(a[5 * 16384 + i * XL_ELEMS:5 * 16384 + (i + 1) * XL_ELEMS])
+    lin = torch.zeros(128 * 128, dtype=torch.float64, device=dev)
+    D._lib.call("dhqr_debug_copy_f64", h.raw, b"linv", vp(lin), lin.numel(), sp())
+    torch.cuda.synchronize()
+    out["Tt"] = lin.cpu().numpy().reshape(128, 128).T.copy()
     return out
 
 
@@ -102,6 +106,9 @@ def test_stage_outputs_against_the_numpy_model(D, dev, oracle):
     Hm, am, okm = W.wide_panel(P)
     assert okm and np.abs(H - Hm).max() < 1e-9 and np.abs(al - am).max() < 1e-9 * np.abs(am).max()
     assert oracle.qr_residual(P, np.asfortranarray(H), al) < TOL_RES
+    # k_trecon: T' from the reconstruction == (I + stril(V'V))^{-1} (what k_tinv computes from the Gram matrix)
+    assert np.abs(st["Tt"] - W.gram_T(H)).max() < 1e-13, "k_hr128 (MT) / k_trecon"
+    assert np.abs(np.triu(st["Tt"], 1)).max() == 0.0
 
 
 def test_loss_of_orthogonality_beyond_first_order_refuses_the_panel(D, dev, oracle):

@@ -29,6 +29,17 @@ def test_same_reflectors_as_the_reference_recurrences(oracle, m):
     assert np.abs((V * V).sum(0) - 2.0).max() < 1e-13            # |v|^2 = 2 (S:131-135)
 
 
+def test_compact_wy_factor_from_the_reconstruction(oracle):
+    P = oracle.np_uniform(8, 2048, 128)
+    R1, _ = W.cholesky_upper(P.T @ P)
+    Q1 = W.solve_right(P, W.inverse_operand(R1))
+    R2, Z2, ok = W.second_pass(Q1.T @ Q1)
+    Wt, Sg, Ud = W.signed_lu(W.solve_right(Q1[:128], Z2))
+    H, a, ok = W.wide_panel(P)
+    Tt = W.reconstruction_T(H, Wt, Sg, Ud)
+    assert np.abs(Tt - W.gram_T(H)).max() < 1e-14 and np.abs(np.triu(Tt, 1)).max() < 1e-15
+
+
 def test_blocked_sweep_matches_oracle(oracle):
     A = oracle.np_uniform(0, 1100, 1024)
     H, a, bad = W.blocked_qr(A)

@@ -166,6 +166,15 @@ def wide_panel(P, kappa_max=KAPPA_MAX):
     return H, alpha, True
 
 
+def reconstruction_T(H, Wt, Sg, Ud):
+    """T' from the reconstruction (k_hr128 + k_trecon): V1 T V1' = E - Q S = L_lu U_lu  =>  T' = V1^{-1} (U_lu' D'^{-1}), with
+    U_lu(j, j) = Ud_j, U_lu(j, k) = -Up(j, k) S_k (k > j) and D' = diag(v_jj)."""
+    n = H.shape[1]
+    sq = np.sqrt(Ud)
+    MT = np.diag(-Sg * sq) + np.tril((np.triu(Wt, 1) * Sg[None, :] * (Sg / sq)[:, None]).T, -1)
+    return np.linalg.solve(np.tril(H[:n]), MT)
+
+
 def gram_T(H):
     """T' from the Gram matrix, as k_tinv does: T^{-1} = I + striu(V'V)."""
     n = H.shape[1]
