@@ -120,6 +120,9 @@ struct dhqr_context {
     cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
+    cudaStream_t aux_stream = nullptr;                                  // small side kernels of the wide chain (Rt = R2 R1, k_trecon), high priority
+    cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    int wide_aux = 1;                                                   // option: run them beside the chain instead of inside it
     cudaStream_t hp2_stream = nullptr;                                  // the chain's second apply (V_k -> columns of panel k+2), high priority
     int wide_trecon = 1;                                                // option: T' of a wide panel from the reconstruction (k_trecon)
     int host_trace = 0;                                                 // option: print a stage timeline of dhqr_qr_host_f64 to stderr
@@ -589,22 +592,31 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
     pre(c, st);
     k_gram2_finish<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, w.wsum, R2, Z2, c->wctl, step, vflag);
     TRY(post(c, st, "k_gram2_finish"));
-    pre(c, st);
-    k_trimm128<<<10, 256, SMEM_TRIMM, st>>>(R2, R1, Rt, c->wctl, step);
-    TRY(post(c, st, "k_trimm128"));
+    // Two small kernels sit beside the chain, not in it (their own high-priority stream, unless the per-launch profile or the
+    // debug sync asks for plain stream order): Rt = R2 R1 overlaps the solve of the top chunks, k_trecon the last pass
+    cudaStream_t sx = (c->wide_aux && !c->profile && !c->sync) ? c->aux_stream : st;
+    if (sx != st) { CU(cudaEventRecord(c->ev_aux[0], st)); CU(cudaStreamWaitEvent(sx, c->ev_aux[0], 0)); }
+    pre(c, sx);
+    k_trimm128<<<10, 256, SMEM_TRIMM, sx>>>(R2, R1, Rt, c->wctl, step);
+    TRY(post(c, sx, "k_trimm128"));
+    if (sx != st) CU(cudaEventRecord(c->ev_aux[1], sx));
     TRY(rmul(0, 2, Z2, nullptr));
+    if (sx != st) CU(cudaStreamWaitEvent(st, c->ev_aux[1], 0));
     pre(c, st);
     k_hr128<<<1, 512, SMEM_WIDE1, st>>>(vpk, Rt, P, lda, alpha + p.c, Rr, MT, c->wctl, step, stamps ? stamps + 16 : nullptr);
     TRY(post(c, st, "k_hr128"));
     if (linv_out) {     // T' of the panel from the reconstruction: the owner's next block update needs neither V'V nor k_tinv
-        pre(c, st);
-        k_trecon<<<4, 256, SMEM_TRECON, st>>>(vpk, MT, linv_out, c->wctl, step);
-        TRY(post(c, st, "k_trecon"));
+        if (sx != st) { CU(cudaEventRecord(c->ev_aux[2], st)); CU(cudaStreamWaitEvent(sx, c->ev_aux[2], 0)); }
+        pre(c, sx);
+        k_trecon<<<4, 256, SMEM_TRECON, sx>>>(vpk, MT, linv_out, c->wctl, step);
+        TRY(post(c, sx, "k_trecon"));
+        if (sx != st) CU(cudaEventRecord(c->ev_aux[3], sx));
     }
     pre(c, st);
     k_trimm_z<<<10, 256, SMEM_TRIMM, st>>>(Rr, R2, Z23, c->wctl, step);
     TRY(post(c, st, "k_trimm_z"));
     TRY(rmul(2, nq - 2, Z23, P));
+    if (linv_out && sx != st) CU(cudaStreamWaitEvent(st, c->ev_aux[3], 0));   // T' is part of the panel's result
     c->wide_panels++;
     return 0;
 }
@@ -1055,6 +1067,8 @@ static int create_common(dhqr_handle* h, int device) {
         CU(cudaStreamCreateWithPriority(&c->hp_lo, cudaStreamNonBlocking, lo));
         CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&c->hp2_stream, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
         c->hp_stream = c->hp_hi;
     }
     *h = c;
@@ -1106,6 +1120,9 @@ int dhqr_destroy(dhqr_handle c) {
     if (c->hp_lo) cudaStreamDestroy(c->hp_lo);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->hp2_stream) cudaStreamDestroy(c->hp2_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
     cudaFree(c->v1); cudaFree(c->xbuf); cudaFree(c->hostA); cudaFree(c->hostB); cudaFree(c->d_i64);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -1140,6 +1157,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp_stream = value ? c->hp_hi : c->hp_lo;
     } else if (!strcmp(key, "hp_max_ctas")) {
         c->hp_max_ctas = (int)value;
+    } else if (!strcmp(key, "wide_aux")) {
+        c->wide_aux = value ? 1 : 0;
     } else if (!strcmp(key, "wide_trecon")) {
         c->wide_trecon = value ? 1 : 0;
     } else if (!strcmp(key, "host_trace")) {

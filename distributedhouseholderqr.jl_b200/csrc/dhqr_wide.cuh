@@ -104,16 +104,20 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
     __syncthreads();
     if (stamps && tid == 0) stamps[0] = clock64() - t0;
     if (!*sbad) {
+        double dcur = 1.0, rcur = 1.0;                 // pivot of the row this warp publishes next and its rsqrt
 #pragma unroll
         for (int aj = 0; aj < 8; ++aj) {
             const int bj = aj >> 1;
+            if (warp == 0) {                           // first row of the block of 16: nothing to overlap the rsqrt with
+                dcur = __shfl_sync(0xffffffffu, g[aj][bj], (aj & 1) * 16);
+                rcur = rsqrt_nb(dcur);
+            }
 #pragma unroll 1
             for (int t = 0; t < 16; ++t) {
                 const int j = 16 * aj + t, lj = (aj & 1) * 16 + t;
                 double* rb = rowbuf + (j & 1) * WP;
                 if (warp == t) {                       // this warp holds row j in g[aj][*]
-                    const double d = __shfl_sync(0xffffffffu, g[aj][bj], lj);
-                    const double ri = rsqrt_nb(d);
+                    const double d = dcur, ri = rcur;
                     if (lane == 0) {
                         if (!(d > 0.0) || !(d < 1e300)) *sbad = 1;
                         rinv[j] = ri;
@@ -136,6 +140,12 @@ __global__ void __launch_bounds__(512, 1) k_chol128(const double* __restrict__ G
                         const double rr = rb[warp + 16 * a];
 #pragma unroll
                         for (int b = bj; b < 4; ++b) g[a][b] -= rr * rc[b];
+                        if (a == aj && warp == t + 1) {
+                            // this warp publishes row j + 1 next: its pivot is final now; the rsqrt (the long dependent chain of a
+                            // step) runs while the warp updates its other rows instead of after the next barrier
+                            dcur = __shfl_sync(0xffffffffu, g[aj][bj], lj + 1);
+                            rcur = rsqrt_nb(dcur);
+                        }
                     }
             }
         }
@@ -472,6 +482,7 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
     double* rsq = Ud + WP;
     double* colbuf = rsq + WP;                           // [2][128]
     double* rowbuf = colbuf + 2 * WP;                    // [2][128]
+    double* fb = rowbuf + 2 * WP;                        // [2]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (wide_gate_closed(ctl, step) || ctl->status) return;
     const long long t0 = clock64();
@@ -486,9 +497,16 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
 #pragma unroll
         for (int b = 0; b < 4; ++b) w[a][b] = Wt[(warp + 16 * a) * WLD + lane + 32 * b];
     if (stamps && tid == 0) stamps[4] = clock64() - t0;
+    double fcur = 0.0, scur = 0.0, ucur = 1.0;         // S_j / U_jj, S_j, U_jj of the pivot this thread publishes next
 #pragma unroll
     for (int aj = 0; aj < 8; ++aj) {
         const int bj = aj >> 1;
+        if (warp == 0 && lane == (aj & 1) * 16) {          // first pivot of the block of 16
+            const double pv = w[aj][bj];
+            scur = pv > 0.0 ? -1.0 : 1.0;
+            ucur = 1.0 + fabs(pv);
+            fcur = scur / ucur;
+        }
 #pragma unroll 1
         for (int t = 0; t < 16; ++t) {
             const int j = 16 * aj + t, lj = (aj & 1) * 16 + t;
@@ -501,13 +519,10 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
             if (warp == t) {
 #pragma unroll
                 for (int b = bj; b < 4; ++b) rb[lane + 32 * b] = w[aj][b];
+                if (lane == lj) { fb[j & 1] = fcur; Sg[j] = scur; Ud[j] = ucur; }
             }
             __syncthreads();
-            const double pv = rb[j];
-            const double sgn = pv > 0.0 ? -1.0 : 1.0;
-            const double u = 1.0 + fabs(pv);
-            if (tid == 0) { Sg[j] = sgn; Ud[j] = u; }
-            const double f = sgn / u;
+            const double f = fb[j & 1];
             double rc[4];
 #pragma unroll
             for (int b = bj; b < 4; ++b) rc[b] = rb[lane + 32 * b];
@@ -518,6 +533,13 @@ __global__ void __launch_bounds__(512, 1) k_hr128(double* __restrict__ vpk, cons
 #pragma unroll
                     for (int b = bj; b < 4; ++b)
                         if (b > bj || lane > lj) w[a][b] += li * rc[b];
+                    if (a == aj && warp == t + 1 && lane == lj + 1) {
+                        // the next pivot is final: its division runs while this thread updates its other rows
+                        const double pv = w[aj][bj];
+                        scur = pv > 0.0 ? -1.0 : 1.0;
+                        ucur = 1.0 + fabs(pv);
+                        fcur = scur / ucur;
+                    }
                 }
         }
     }
