@@ -1510,6 +1510,7 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     CU(cudaSetDevice(c->device));
     const int64_t ldd = rup(m, 32);                       // padded device leading dimension (aligned TMA sources)
     TRY(ensure(&c->hostA, &c->hostA_elems, (size_t)ldd * n + (size_t)n));
+    TRY(ensure_workspace(c, m, n));       // once, for the full width: growing it between the two halves would synchronise the device
     double* dA = c->hostA;
     double* dal = c->hostA + (size_t)ldd * n;
     cudaStream_t st = c->copy_stream;

@@ -114,4 +114,38 @@ function LinearAlgebra.:(\)(H::DistributedHouseholderQRStruct{<:DArray}, b::Abst
     return xs[1]
 end
 
+# ---- ComplexF64 (the reference's second element type, test/runtests.jl:43; S:9, S:51-59, S:162-196), single GPU ----
+function qr!(A::CuMatrix{ComplexF64})
+    m, n = size(A)
+    α = CUDA.zeros(ComplexF64, n)
+    GC.@preserve A α check(:dhqr_qr_c64, ccall((:dhqr_qr_c64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, CuPtr{ComplexF64}, Int64, CuPtr{ComplexF64}, Ptr{Cvoid}),
+        handle().ptr, m, n, 0, n, pointer(A), stride(A, 2), pointer(α), stream_ptr()))
+    return DistributedHouseholderQRStruct(A, α)
+end
+function LinearAlgebra.:(\)(H::DistributedHouseholderQRStruct{<:CuMatrix{ComplexF64}}, b::AbstractVector)
+    A = H.A; m, n = size(A)
+    s = CuVector{ComplexF64}(b)                                                          # S:318
+    GC.@preserve A s check(:dhqr_solve_c64, ccall((:dhqr_solve_c64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, CuPtr{ComplexF64}, Int64, CuPtr{ComplexF64}, CuPtr{ComplexF64}, Int64, Cint, Ptr{Cvoid}),
+        handle().ptr, m, n, 0, n, pointer(A), stride(A, 2), pointer(H.α), pointer(s), m, 1, stream_ptr()))
+    return Array(s[1:n])                                                                 # S:320
+end
+
+# ---- Q'b and Q b as operators (not in the reference, which never forms Q) ----
+function apply_qt!(b::CuVecOrMat{Float64}, A::CuMatrix{Float64})
+    m, n = size(A)
+    GC.@preserve A b check(:dhqr_apply_qt_f64, ccall((:dhqr_apply_qt_f64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, CuPtr{Float64}, Int64, CuPtr{Float64}, Int64, Cint, Ptr{Cvoid}),
+        handle().ptr, m, n, 0, n, pointer(A), stride(A, 2), pointer(b), max(stride(b, 2), m), size(b, 2), stream_ptr()))
+    return b
+end
+function apply_q!(b::CuVecOrMat{Float64}, A::CuMatrix{Float64})
+    m, n = size(A)
+    GC.@preserve A b check(:dhqr_apply_q_f64, ccall((:dhqr_apply_q_f64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, CuPtr{Float64}, Int64, CuPtr{Float64}, Int64, Cint, Ptr{Cvoid}),
+        handle().ptr, m, n, 0, n, pointer(A), stride(A, 2), pointer(b), max(stride(b, 2), m), size(b, 2), stream_ptr()))
+    return b
+end
+
 end # module

@@ -178,6 +178,25 @@ def test_empty_and_degenerate_inputs(D, dev):
     assert e.value.code == -3
 
 
+def test_exact_zero_pivot_is_a_documented_divergence(D, dev, oracle):
+    # alphafactor(0) = -sign(0) = 0 (S:8): with an exactly zero pivot the reference sets alpha = 0, its "reflector" has |v|^2 = 1
+    # and the factorisation is garbage (later a division by zero).  The unblocked path mirrors that literally; the blocked paths
+    # (Householder reconstruction picks the sign of a zero pivot as +) return a VALID factorisation instead - pinned here.
+    for m, n in ((300, 40), (1024, 256)):                     # narrow chain / wide chain
+        A0 = oracle.np_uniform(17, m, n)
+        A0[0, 0] = 0.0
+        A = D.to_colmajor(A0, dev)
+        H = D.qr_(A)
+        Hg, ag = A.cpu().numpy(), H.α.cpu().numpy()
+        assert np.isfinite(Hg).all() and oracle.qr_residual(A0, np.asfortranarray(Hg), ag) < TOL_RES
+        assert abs(abs(ag[0]) - np.linalg.norm(A0[:, 0])) < 1e-12 * np.linalg.norm(A0[:, 0])
+        Hr, ar = oracle.np_qr(A0)                                 # the reference's recurrences on the same input
+        assert ar[0] == 0.0 and not oracle.qr_residual(A0, Hr, ar) < 1e-3
+        A1 = D.to_colmajor(A0, dev)
+        H1 = D.qr_(A1, nb=1)                                      # the literal column loop reproduces the reference
+        assert float(H1.α[0]) == 0.0
+
+
 def test_multiple_right_hand_sides(D, dev, oracle, coracle):
     m, n, k = 700, 90, 5
     A0 = coracle.fill_uniform(4, m, n)
