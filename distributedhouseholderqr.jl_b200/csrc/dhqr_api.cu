@@ -141,6 +141,8 @@ struct dhqr_context {
     int bs_wave_max_ctas = 0;                                           // co-residency limit of k_backsolve_wave on this device
     unsigned long long* bs_cells = nullptr; size_t bs_cells_blocks = 0; // x cells of the wavefront ([block][32][2 words])
     uint32_t bs_epoch = 0;
+    int unblocked_wave = 1;                                             // nb = 1, m <= 8192: the column loop as one persistent launch
+    unsigned int* uw_flags = nullptr; size_t uw_flags_n = 0; unsigned int uw_epoch = 0;
     int fuse_house = 1;                                                 // nb = 1: next reflector formed inside the apply kernel (one launch per column)
     int cvy_persist = 1;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
@@ -920,6 +922,26 @@ static int qr_unblocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, 
     TRY(check_partition(col0s, nls, n));
     TRY(ensure_workspace(c, m, nl));
     const int64_t lend = col0 + nl;
+    if (c->nranks == 1 && n > 0 && m <= (int64_t)UW_MAXI * UW_THREADS && c->unblocked_wave && !c->profile && !c->sync) {
+        // single GPU, short columns: the whole column loop as one persistent cooperative launch (k_unblocked_wave)
+        if (c->uw_flags_n < (size_t)n) {
+            if (c->uw_flags) CU(cudaFree(c->uw_flags));
+            c->uw_flags = nullptr;
+            CU(cudaMalloc((void**)&c->uw_flags, sizeof(unsigned int) * (size_t)(n + 64)));
+            CU(cudaMemset(c->uw_flags, 0, sizeof(unsigned int) * (size_t)(n + 64)));
+            c->uw_flags_n = (size_t)n + 64;
+            c->uw_epoch = 0;
+        }
+        if (c->uw_epoch > 0xFFFFFFF0u) { CU(cudaMemsetAsync(c->uw_flags, 0, sizeof(unsigned int) * c->uw_flags_n, st)); c->uw_epoch = 0; }
+        const unsigned int tag = ++c->uw_epoch;
+        int nn = (int)n;
+        void* args[] = {&A, &lda, &m, &nn, &alpha, &c->uw_flags, (void*)&tag};
+        const int G = (int)std::min<int64_t>(c->sms, n);
+        pre(c, st);
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)k_unblocked_wave, dim3(G), dim3(UW_THREADS), args, 0, st);
+        if (e != cudaSuccess) return set_err(1000 + (int)e, "cooperative launch of k_unblocked_wave failed: %s", cudaGetErrorString(e));
+        return post(c, st, "k_unblocked_wave", 16.0 * (double)m * n * n / 2);
+    }
     if (c->nranks == 1 && n > 0 && (size_t)((m + 2) & ~(int64_t)1) * 8 * (A1_CW + 1) <= 200 * 1024 && c->fuse_house) {
         // single GPU, the column tile fits in shared memory: one launch per column step (the next reflector is formed by the
         // CTA that has just updated its column, k_apply1_tma), two v buffers alternating between steps
@@ -1114,6 +1136,7 @@ int dhqr_destroy(dhqr_handle c) {
         if (b < 2) cudaFree(c->vpk2[b]);
         cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
+    cudaFree(c->uw_flags);
     cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps); cudaFree(c->bs_cells);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
@@ -1167,6 +1190,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->hp2 = value ? 1 : 0;
     } else if (!strcmp(key, "bs_wave")) {
         c->bs_wave = value ? 1 : 0;
+    } else if (!strcmp(key, "unblocked_wave")) {
+        c->unblocked_wave = value ? 1 : 0;
     } else if (!strcmp(key, "fuse_house")) {
         c->fuse_house = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_persist")) {

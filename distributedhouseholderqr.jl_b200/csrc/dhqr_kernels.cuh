@@ -1828,6 +1828,123 @@ __global__ void __launch_bounds__(A1_THREADS) k_apply1_direct(const double* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// unblocked path as ONE persistent launch (single GPU, m <= UW_MAXI * UW_THREADS rows): the whole column loop S:127-144.
+//   CTA g owns the columns c == g (mod G) for the whole factorisation.  Step j: every CTA waits for "v_j is in place"
+//   (a release/acquire flag per column), reads v_j = A[j:m, j] into registers, and for each of its columns c > j reads the
+//   column tail into registers, forms s = v'a (S:208, warp shuffles + one block reduction) and writes back a - v s (S:209).
+//   The CTA that owns column j+1 takes it first and runs S:129-135 on it straight away (norm, alpha, scale: the next
+//   reflector), publishes it and only then turns to its other columns: the reflector chain never waits for the trailing update.
+//   No grid barrier: columns are private to their CTA, the only cross-CTA dependency is the reflector itself.
+//   Everything streams L2 <-> registers (the 64 MiB matrix of BASELINE config 2 is L2 resident); CTAs spin on the flags, so all
+//   of them must be resident: cooperative launch, G <= #SMs.
+// ------------------------------------------------------------------------------------------------
+constexpr int UW_THREADS = 256;
+constexpr int UW_MAXI = 32;            // rows per thread: m <= 8192
+__global__ void __launch_bounds__(UW_THREADS, 1) k_unblocked_wave(double* __restrict__ A, int64_t lda, int64_t m, int n,
+                                                                  double* __restrict__ alpha, unsigned int* flags, unsigned int tag) {
+    __shared__ double red[2][UW_THREADS / 32];
+    __shared__ double hs[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, g = blockIdx.x;
+    int slot = 0;
+    auto block_sum = [&](double v) {             // fixed order: deterministic
+        v = warp_sum(v);
+        if (lane == 0) red[slot][warp] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < UW_THREADS / 32; ++w) t += red[slot][w];
+        slot ^= 1;
+        return t;
+    };
+    // S:129-135 on the column tail x[] (rows r0 + tid + UW_THREADS i, i.e. rows >= r0) held in registers; writes alpha[jn]
+    auto house = [&](double (&x)[UW_MAXI], int64_t r0, int jn) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < UW_MAXI; ++i) {
+            const int64_t r = r0 + tid + (int64_t)UW_THREADS * i;
+            if (r >= jn && r < m) acc += x[i] * x[i];
+        }
+        const double t = block_sum(acc);
+        if (tid == (int)(jn - r0)) {             // the thread that holds row jn (jn - r0 is 0 or 1)
+            const double x0 = x[0];
+            const double sn = sqrt(t);
+            const double sg = x0 > 0.0 ? 1.0 : (x0 < 0.0 ? -1.0 : 0.0);
+            const double al = -sg * sn;
+            alpha[jn] = al;
+            hs[0] = al;
+            hs[1] = 1.0 / sqrt(sn * (sn + fabs(x0)));
+        }
+        __syncthreads();
+        const double al = hs[0], f = hs[1];
+#pragma unroll
+        for (int i = 0; i < UW_MAXI; ++i) {
+            const int64_t r = r0 + tid + (int64_t)UW_THREADS * i;
+            if (r >= jn && r < m) x[i] = (r == jn ? x[i] - al : x[i]) * f;
+        }
+    };
+    auto publish = [&](int j) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + j), "r"(tag) : "memory");
+    };
+    if (g == 0) {                                // column 0: nothing to apply first
+        double x[UW_MAXI];
+#pragma unroll
+        for (int i = 0; i < UW_MAXI; ++i) {
+            const int64_t r = tid + (int64_t)UW_THREADS * i;
+            x[i] = r < m ? A[r] : 0.0;
+        }
+        house(x, 0, 0);
+#pragma unroll
+        for (int i = 0; i < UW_MAXI; ++i) {
+            const int64_t r = tid + (int64_t)UW_THREADS * i;
+            if (r < m) A[r] = x[i];
+        }
+        publish(0);
+    }
+    for (int j = 0; j + 1 < n; ++j) {
+        int c = j + 1 + ((g - (j + 1)) % G + G) % G;        // this CTA's first column right of j
+        if (c >= n) continue;                                // (its later steps have nothing either, but the loop is cheap)
+        if (tid == 0) {
+            unsigned int f;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + j) : "memory");
+            } while (f != tag);
+        }
+        __syncthreads();
+        double v[UW_MAXI];
+        const double* vj = A + (int64_t)j * lda;
+#pragma unroll
+        for (int i = 0; i < UW_MAXI; ++i) {
+            const int64_t r = j + tid + (int64_t)UW_THREADS * i;
+            v[i] = r < m ? __ldcg(vj + r) : 0.0;      // written by another SM a moment ago: read it from L2, never from this SM's L1
+        }
+        for (; c < n; c += G) {
+            double* col = A + (int64_t)c * lda;
+            double x[UW_MAXI];
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < UW_MAXI; ++i) {
+                const int64_t r = j + tid + (int64_t)UW_THREADS * i;
+                x[i] = r < m ? __ldcg(col + r) : 0.0;
+                acc += v[i] * x[i];                                                   // S:208 partialdot
+            }
+            const double s = block_sum(acc);
+#pragma unroll
+            for (int i = 0; i < UW_MAXI; ++i) x[i] -= v[i] * s;                       // S:209 hotloop!
+            if (c == j + 1) house(x, j, j + 1);                                       // the next reflector, at once
+#pragma unroll
+            for (int i = 0; i < UW_MAXI; ++i) {
+                const int64_t r = j + tid + (int64_t)UW_THREADS * i;
+                if (r < m) col[r] = x[i];
+            }
+            if (c == j + 1) publish(j + 1);
+        }
+    }
+}
+
 // partialdot (S:42-49) as a standalone primitive: one CTA, warp-shuffle tree.
 __global__ void __launch_bounds__(1024, 1) k_partialdot(const double* __restrict__ x, const double* __restrict__ y,
                                                         int64_t i0, int64_t i1, double* __restrict__ out) {
