@@ -1906,7 +1906,17 @@ __global__ void __launch_bounds__(UW_THREADS, 1) k_unblocked_wave(double* __rest
     }
     for (int j = 0; j + 1 < n; ++j) {
         int c = j + 1 + ((g - (j + 1)) % G + G) % G;        // this CTA's first column right of j
-        if (c >= n) continue;                                // (its later steps have nothing either, but the loop is cheap)
+        if (c >= n) break;                                   // nothing left for this CTA: its later steps are empty as well
+        double x[UW_MAXI];
+        if (c == j + 1) {                                    // the next pivot column is ours: fetch it while v_j is still on its way
+            __syncthreads();                                 // (the rows were written by other threads of this CTA in the step before)
+            const double* col = A + (int64_t)c * lda;
+#pragma unroll
+            for (int i = 0; i < UW_MAXI; ++i) {
+                const int64_t r = j + tid + (int64_t)UW_THREADS * i;
+                x[i] = r < m ? __ldcg(col + r) : 0.0;
+            }
+        }
         if (tid == 0) {
             unsigned int f;
             do {
@@ -1923,12 +1933,11 @@ __global__ void __launch_bounds__(UW_THREADS, 1) k_unblocked_wave(double* __rest
         }
         for (; c < n; c += G) {
             double* col = A + (int64_t)c * lda;
-            double x[UW_MAXI];
             double acc = 0.0;
 #pragma unroll
             for (int i = 0; i < UW_MAXI; ++i) {
                 const int64_t r = j + tid + (int64_t)UW_THREADS * i;
-                x[i] = r < m ? __ldcg(col + r) : 0.0;
+                if (c != j + 1) x[i] = r < m ? __ldcg(col + r) : 0.0;
                 acc += v[i] * x[i];                                                   // S:208 partialdot
             }
             const double s = block_sum(acc);
