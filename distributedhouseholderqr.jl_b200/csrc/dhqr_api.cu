@@ -144,7 +144,6 @@ struct dhqr_context {
     int unblocked_wave = 1;                                             // nb = 1, m <= 8192: the column loop as one persistent launch
     unsigned int* uw_flags = nullptr; size_t uw_flags_n = 0; unsigned int uw_epoch = 0;
     int fuse_house = 1;                                                 // nb = 1: next reflector formed inside the apply kernel (one launch per column)
-    int cvy_q = 1;                                                      // 128-wide gemm_cvy: four k-stages of 16 (k_gemm_cvy_q) instead of two of 32
     int cvy_persist = 1;                                                // 128-wide gemm_cvy: consecutive tiles per CTA (0: one-tile kernel)
     int cvy_defer = 1;                                                  // 128-wide gemm_cvy: C tile read in batches behind the k-stages
     int cvy_warps = 8;                                                  // MMA warps per gemm_cvy CTA (4: 64x32 warp tiles, 8: 32x32)
@@ -215,8 +214,6 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(K_G2W, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_gemm_cvy_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CVYQ));
-    CU(cudaFuncSetAttribute(k_gemm_cvy_q, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
@@ -262,7 +259,7 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
         // set 2 only ever updates the <= 128 columns of one panel: a quarter of the split-K partial buffer is plenty
         TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)(b < 2 ? std::max(WPART_TILES, tiles_max) : WPART_TILES / 4) * NBMAX * G1_BN));
         TRY(ensure(&w.wsum, &w.wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
-        TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)std::max((NBMAX / KC) * YT * LDK, (NBMAX / KCQ) * YT * LDKQ) * ((n_local_max + YT - 1) / YT + 2)));
+        TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
         TRY(ensure(&w.linv, &w.linv_elems, (size_t)NBMAX * NBMAX));
     }
     for (int b = 0; b < 3; ++b)
@@ -363,7 +360,6 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     if (ncols <= 0 || rows <= 0) return 0;
     const bool small = (nbp <= 32);
     const int NBPK = small ? 32 : 128;          // kernel instantiation
-    const bool use_q = !small && c->cvy_q && c->cvy_warps == 8 && rup(nbp, KC) / KC == 4 && c->cvy_persist > 0;   // k_gemm_cvy_q
     const int bn = small ? G1S_BN : G1_BN;
     const int nv = reuse_T ? 0 : NBPK;
     const int next = nv + ncols;
@@ -404,8 +400,8 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
             TRY(post(c, st, small ? "k_tinv32" : "k_tinv128"));
         }
         pre(c, st);
-        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans, KC);
-        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans, use_q ? KCQ : KC);
+        if (small) k_ymake<32><<<ygrid, 256, smem_ymake(32), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans);
+        else k_ymake<128><<<ygrid, 256, smem_ymake(128), st>>>(w.wsum, nv, ncols, linv, w.ypk, trans);
         TRY(post(c, st, small ? "k_ymake32" : "k_ymake128"));
     }
     pre(c, st);
@@ -418,9 +414,7 @@ static int apply_block_reflector(dhqr_context* c, cudaStream_t st, const double*
     dim3 grid2((unsigned)((rows + G2_BM - 1) / G2_BM), (unsigned)((ncols + G2_BN - 1) / G2_BN));
     g2.tiles_m = (int)grid2.x; g2.tiles_n = (int)grid2.y;
     g2.tiles_per_cta = c->cvy_persist;
-    if (use_q)
-        k_gemm_cvy_q<<<(g2.tiles_m * g2.tiles_n + c->cvy_persist - 1) / c->cvy_persist, 9 * 32, SMEM_CVYQ, st>>>(g2);
-    else if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_persist > 0)
+    if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_persist > 0)
         k_gemm_cvy_p<<<(g2.tiles_m * g2.tiles_n + c->cvy_persist - 1) / c->cvy_persist, 9 * 32, smem_g2(), st>>>(g2);
     else if (c->cvy_warps == 8 && g2.nkq == 4 && c->cvy_defer) K_G2D<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
     else if (c->cvy_warps == 8) K_G2W<<<grid2, 9 * 32, smem_g2(), st>>>(g2);
@@ -1200,8 +1194,6 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->unblocked_wave = value ? 1 : 0;
     } else if (!strcmp(key, "fuse_house")) {
         c->fuse_house = value ? 1 : 0;
-    } else if (!strcmp(key, "cvy_q")) {
-        c->cvy_q = value ? 1 : 0;
     } else if (!strcmp(key, "cvy_persist")) {
         if (value < 0 || value > 1 << 20) return set_err(-3, "cvy_persist out of range");
         c->cvy_persist = (int)value;

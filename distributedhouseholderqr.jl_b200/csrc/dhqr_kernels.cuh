@@ -627,134 +627,6 @@ __global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_p(GemmCvyArgs a) {
     // the last stage of the last tile is never released: nobody waits for it
 }
 
-// ------------------------------------------------------------------------------------------------
-// gemm_cvy_q: k_gemm_cvy_p with a DEEPER, FINER operand pipeline: k-stages of KCQ = 16 instead of 32 and four of them in
-// flight instead of two, in the same shared memory.  The source-level ncu profile of k_gemm_cvy_p (profiles/r02_prof_cvy_ncu.txt)
-// puts half of its long-scoreboard stalls on the branch of the mbarrier wait: with two stages released one iteration late the
-// producer is exactly one stage ahead, and every CTA starts with an empty pipeline.  Here it is three stages ahead.
-// The C tile is read one half 8-row block per stage (8 stages = 4 blocks x 2 halves).  ypk must be in the KCQ chunk layout.
-// ------------------------------------------------------------------------------------------------
-constexpr int KCQ = 16, LDKQ = KCQ + 4, QSTAGES = 4;
-constexpr size_t SMEM_CVYQ = (size_t)QSTAGES * (2 * KCQ * LD1 + YT * LDKQ) * 8 + 2 * QSTAGES * 8;
-
-__global__ void __launch_bounds__(9 * 32, 2) k_gemm_cvy_q(GemmCvyArgs a) {
-    constexpr int BM = 128, BN = YT, WM = 4, WN = 2, NCW = WM * WN, STAGES = QSTAGES;
-    constexpr int WTM = BM / WM, WTN = BN / WN;
-    constexpr int MI = WTM / 8, NJ = WTN / 8, NH = NJ / 2;
-    constexpr int VH = KCQ * LD1;   // doubles per 64-row x 16-col slice
-    constexpr int NIT = 128 / KCQ;  // 8 k-stages per tile
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sV = reinterpret_cast<double*>(smem_raw);   // [STAGES][2][KCQ][LD1]
-    double* sY = sV + STAGES * 2 * VH;                   // [STAGES][BN][LDKQ]
-    uint64_t* full = reinterpret_cast<uint64_t*>(sY + STAGES * BN * LDKQ);
-    uint64_t* empty = full + STAGES;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (wide_gate_closed(a.ctl, a.gate)) return;
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCW);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int ntiles = a.tiles_m * a.tiles_n;
-    const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, ntiles);
-
-    if (warp == NCW) {
-        if (lane == 0) {
-            int g = 0;
-            for (int t = t_lo; t < t_hi; ++t) {
-                const int bx = t % a.tiles_m, by = t / a.tiles_m;
-                const double* v0 = a.vpk + (int64_t)(2 * bx) * VPK_CHUNK + (int64_t)a.voff * LD1;
-                const double* y0 = a.ypk + (int64_t)by * NIT * (BN * LDKQ);
-                for (int it = 0; it < NIT; ++it, ++g) {
-                    const int s = g % STAGES;
-                    mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * VH + BN * LDKQ) * 8));
-                    double* dV = sV + (size_t)s * 2 * VH;
-                    bulk_g2s(dV, v0 + (int64_t)it * VH, VH * 8, &full[s]);
-                    bulk_g2s(dV + VH, v0 + VPK_CHUNK + (int64_t)it * VH, VH * 8, &full[s]);
-                    bulk_g2s(sY + (size_t)s * BN * LDKQ, y0 + (int64_t)it * (BN * LDKQ), BN * LDKQ * 8, &full[s]);
-                }
-            }
-        }
-        return;
-    }
-
-    const int wm = warp / WN, wn = warp % WN;
-    const int fragA = (lane & 3) * LD1 + (lane >> 2);
-    const int fragB = (lane >> 2) * LDKQ + (lane & 3);
-    const double* v0s = sV + (wm * WTM / 64) * VH + (wm * WTM % 64) + fragA;
-    const double* y0s = sY + wn * WTN * LDKQ + fragB;
-    int g = 0;
-    for (int t = t_lo; t < t_hi; ++t) {
-        const int bx = t % a.tiles_m, by = t / a.tiles_m;
-        const int64_t rbase = (int64_t)bx * BM + wm * WTM + (lane >> 2);
-        const int cbase = by * BN + wn * WTN + (lane & 3) * 2;
-        double acc[MI][NJ][2];
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll 1
-        for (int it = 0; it < NIT; ++it, ++g) {
-            const int s = g % STAGES, ib = it >> 1, j0 = (it & 1) * NH;
-            double cpre[NH][2];
-            {
-                const int64_t row = rbase + ib * 8;
-                const bool rok = row >= a.row_lo && row < a.rows;
-#pragma unroll
-                for (int j = 0; j < NH; ++j) {
-                    const int col = cbase + (j0 + j) * 8;
-                    const double* p = a.C + (int64_t)col * a.ldc + row;
-                    cpre[j][0] = (rok && col < a.ncols) ? *p : 0.0;
-                    cpre[j][1] = (rok && col + 1 < a.ncols) ? *(p + a.ldc) : 0.0;
-                }
-            }
-            mbar_wait(&full[s], (g / STAGES) & 1);
-            release_prev_stage(empty, g, STAGES, lane);
-            const double* v = v0s + (size_t)s * 2 * VH;
-            const double* y = y0s + (size_t)s * BN * LDKQ;
-#pragma unroll
-            for (int kk = 0; kk < KCQ / 4; ++kk) {
-                double af[MI], bf[NJ];
-#pragma unroll
-                for (int i = 0; i < MI; ++i) af[i] = v[kk * 4 * LD1 + i * 8];
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) bf[j] = y[j * 8 * LDKQ + kk * 4];
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (i == ib && h * NH == j0) {
-#pragma unroll
-                        for (int j = 0; j < NH; ++j) {
-                            acc[i][h * NH + j][0] += cpre[j][0];
-                            acc[i][h * NH + j][1] += cpre[j][1];
-                        }
-                    }
-        }
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-            const int64_t row = rbase + i * 8;
-            const bool rok = row >= a.row_lo && row < a.rows;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int col = cbase + j * 8;
-                double* p = a.C + (int64_t)col * a.ldc + row;
-                if (rok && col < a.ncols) *p = acc[i][j][0];
-                if (rok && col + 1 < a.ncols) *(p + a.ldc) = acc[i][j][1];
-            }
-        }
-    }
-}
-
 constexpr int WP = 128;            // wide panel width
 constexpr int WLD = WP + 1;        // leading dimension of the row-major 128 x 128 work matrices in shared memory
 
@@ -973,7 +845,7 @@ __global__ void __launch_bounds__(512, 1) k_mid32(const double* __restrict__ Wp,
 // ------------------------------------------------------------------------------------------------
 template <int NBP>
 __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws, int woff, int na, const double* __restrict__ Linv,
-                                                  double* __restrict__ ypk, int trans, int kc) {
+                                                  double* __restrict__ ypk, int trans) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sL = reinterpret_cast<double*>(smem_raw);   // [NBP][NBP] col-major
     double* sW = sL + NBP * NBP;                         // [YCOLS][NBP]
@@ -988,7 +860,7 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws,
     __syncthreads();
     constexpr int TPR = 256 / NBP;           // threads per row (2 for 128, 8 for 32)
     constexpr int CPT = YCOLS / TPR;         // columns per thread
-    const int nkq = NBP / kc, ldk = kc + 4;   // k-chunk of the consumer: KC (32) or KCQ (16, k_gemm_cvy_q)
+    constexpr int NKQ = NBP / KC;
     const int i = tid % NBP, jh = tid / NBP;
     double acc[CPT];
 #pragma unroll
@@ -1009,7 +881,7 @@ __global__ void __launch_bounds__(256, 1) k_ymake(const double* __restrict__ Ws,
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const int col = c0 + jh * CPT + j;     // columns beyond na get zeros (the tile is copied whole)
-        ypk[((int64_t)(col / YT) * nkq + i / kc) * (YT * ldk) + (col % YT) * ldk + (i % kc)] = (col < na) ? -acc[j] : 0.0;
+        ypk[((int64_t)(col / YT) * NKQ + i / KC) * (YT * LDK) + (col % YT) * LDK + (i % KC)] = (col < na) ? -acc[j] : 0.0;
     }
 }
 
