@@ -224,7 +224,8 @@ def run_ours(args):
         h = D.default_handle(local)
 
     m, n, nb = args.m, args.n, args.nb
-    b = D.splits(world, n)
+    b = D.splits(world, n) if args.split == "even" else [128 * int(round(x / 128.0)) for x in D.balanced_splits(world, n, "trailing")]
+    b[0], b[-1] = 0, n
     c0, nl = b[rank], b[rank + 1] - b[rank]
     flops = qr_flops(m, n)
     K, W = args.steps, args.warmup
@@ -292,7 +293,7 @@ def run_ours(args):
     parity = {"tolerance": 1e-13, "oracle_pin": ORACLE_PIN}
     if not args.no_check:
         try:
-            parity["qr_residual_fro_rel"] = dist_residual(torch, dist, D, last, alpha, m, n, c0, nl, world, rank, dev, h)
+            parity["qr_residual_fro_rel"] = dist_residual(torch, dist, D, last, alpha, m, n, c0, nl, world, rank, dev, h, b)
         except Exception as e:
             sys.stderr.write(f"[bench] residual check failed on rank {rank}: {type(e).__name__}: {e}\n")
             parity["qr_residual_fro_rel"] = "check failed (see stderr)"
@@ -430,7 +431,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": cfg,
-               "impl_details": {"nb": nb or 128, "cols_per_gpu": nl, "wide_panels": h.get_option("wide_panels"),
+               "impl_details": {"nb": nb or 128, "cols_per_gpu": nl, "column_boundaries": b, "split": args.split, "wide_panels": h.get_option("wide_panels"),
                                 "wide_redone": h.get_option("wide_redone"), "baseline_config": args.config},
                "clocks": clocks, "gpu_launches": launches_all, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                "solve": solve, "parity": parity}
@@ -440,7 +441,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def dist_residual(torch, dist, D, Hloc, alpha, m, n, c0, nl, world, rank, dev, h):
+def dist_residual(torch, dist, D, Hloc, alpha, m, n, c0, nl, world, rank, dev, h, bnd):
     """||QR - A0||_F / ||A0||_F.  Every rank rebuilds ITS columns of Q R from all the reflectors (gathered panel by panel from
     their owners) in torch fp64 on the GPU, compares with its regenerated columns of A0, and the squared norms are summed
     over ranks.  Size independent; a wrong or wrongly ordered V anywhere shows up here (unlike a column-norm check)."""
@@ -451,7 +452,6 @@ def dist_residual(torch, dist, D, Hloc, alpha, m, n, c0, nl, world, rank, dev, h
     R[:n] = Rtop
     if nl:
         R[gl, torch.arange(nl, device=dev)] = alpha[c0:c0 + nl]
-    bnd = D.splits(world, n)
     panels = []
     for r in range(world):
         for o in range(bnd[r], bnd[r + 1], 128):
@@ -511,6 +511,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--split", default="even", choices=["even", "balanced"],
+                    help="column blocks: DArray default (even) or the reference's load-balanced contiguous split (T:35), rounded to panels")
     args = ap.parse_args()
     dm, dn, dnb = (8192, 1024, 1) if args.config == 2 else (32768, 4096, 0)
     args.m, args.n = args.m or dm, args.n or dn
