@@ -109,14 +109,15 @@ struct dhqr_context {
     // workspace
     // three V buffers (panels k, k+1 and the one being broadcast live at the same time under look-ahead) and two
     // workspace sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
-    double* vpk2[3] = {nullptr, nullptr, nullptr}; size_t vpk_elems[3] = {0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]
+    double* vpk2[4] = {nullptr, nullptr, nullptr, nullptr}; size_t vpk_elems[4] = {0, 0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]; [3]: catch-up of late column chunks (host entry)
     struct WSet {
         double* wpart = nullptr; size_t wpart_elems = 0;                // gemm_vta partials
         double* wsum = nullptr;  size_t wsum_elems = 0;                 // reduced Wext
         double* ypk = nullptr;   size_t ypk_elems = 0;                  // packed Y = -T'W
         double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
-    } ws[3];                                                            // [2]: the chain's second apply (columns of panel k+2) on its own stream
-    double* linv_ring[3] = {nullptr, nullptr, nullptr};               // T' of the outer panels in flight (look-ahead)
+    } ws[4];                                                            // [2]: the chain's second apply (columns of panel k+2) on its own stream; [3]: catch-up (host entry)
+    double* linv_all = nullptr; size_t linv_all_elems = 0;              // T' of every outer panel of the factorisation in flight (look-ahead): slot k = panel k
+    double* tslot(int k) const { return linv_all + (size_t)k * 128 * 128; }
     cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
     cudaStream_t hp_hi = nullptr, hp_lo = nullptr;
     cudaStream_t comm_stream = nullptr;                                 // collectives of the look-ahead schedule (high priority)
@@ -161,6 +162,10 @@ struct dhqr_context {
     double wide_kappa = 1000.0;                                         // guard on ||D R1^{-1}||_F of the first Cholesky factor (option "wide_kappa")
     long long* wstamps = nullptr;                                       // clock64 stamps of the single-CTA kernels (option "wide_trace")
     int wide_trace = 0;
+    // Q'b / Qb with one right-hand side: T' of every local panel (computed before the sweep), per-CTA partials of V'b, y, ticket
+    double* qt_T = nullptr;  size_t qt_T_elems = 0;
+    double* qt_part = nullptr; unsigned int* qt_ticket = nullptr;
+    int qt_vec = 1;                                                     // option: use it (0: the GEMM-shaped block update also for one right-hand side)
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
     double* hostA = nullptr; size_t hostA_elems = 0;                    // device staging for _host_ entry points
@@ -169,7 +174,14 @@ struct dhqr_context {
     int64_t launches = 0;
     cudaStream_t copy_stream = nullptr;      // compute stream of the _host_ entry points
     cudaStream_t d2h_stream = nullptr;       // drains finished panels to the host while the factorisation continues
-    cudaStream_t h2d_stream = nullptr;       // uploads the right half while the left half is being factored
+    cudaStream_t h2d_stream = nullptr;       // uploads the later column chunks while the first ones are being factored
+    cudaStream_t cu_stream = nullptr;        // catch-up: reflectors of finished panels applied to a column chunk that arrived late
+    // dhqr_qr_host_f64 -> look-ahead driver: column chunks still on their way to the device.  Chunk j = global columns [c0, c1),
+    // usable once `ev` has fired, joins the trailing matrix at step `join` (after a catch-up with the reflectors of panels < join)
+    struct UpChunk { int64_t c0, c1; cudaEvent_t ev; int join; };
+    std::vector<UpChunk> up_chunks;
+    int host_chunk = 512;                    // option: columns per upload chunk (0: one upload, no overlap)
+    int host_h2d_gbs = 50, host_tflops = 27; // option: what the join-step planner assumes about the link and the device
     std::vector<cudaEvent_t> panel_events;
     // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
     double* mirror_host = nullptr;
@@ -246,24 +258,26 @@ static int ensure(T** p, size_t* have, size_t need) {
 
 static constexpr int64_t WPART_TILES = 2304;   // capacity of the partial buffer in 128 x 64 tiles (151 MB per set)
 
-static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max) {
+// npanels: outer panels of the factorisation about to run (T' slots of the look-ahead schedule); catchup: also size the fourth
+// V buffer / workspace set (dhqr_qr_host_f64 only)
+static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max, int64_t npanels = 0, bool catchup = false) {
     TRY(set_attrs(c));
     const int64_t vrows = rup(m, 128) + 128;
     if (c->vrows_cap < vrows || !c->vpk2[0]) {
         for (int b = 0; b < 3; ++b) TRY(ensure(&c->vpk2[b], &c->vpk_elems[b], (size_t)(vrows / KC1) * VPK_CHUNK));
         c->vrows_cap = vrows;
     }
+    if (catchup) TRY(ensure(&c->vpk2[3], &c->vpk_elems[3], (size_t)(vrows / KC1) * VPK_CHUNK));
+    TRY(ensure(&c->linv_all, &c->linv_all_elems, (size_t)std::max<int64_t>(npanels, 4) * NBMAX * NBMAX));
     const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < (catchup ? 4 : 3); ++b) {
         auto& w = c->ws[b];
         // set 2 only ever updates the <= 128 columns of one panel: a quarter of the split-K partial buffer is plenty
-        TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)(b < 2 ? std::max(WPART_TILES, tiles_max) : WPART_TILES / 4) * NBMAX * G1_BN));
+        TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)(b != 2 ? std::max(WPART_TILES, tiles_max) : WPART_TILES / 4) * NBMAX * G1_BN));
         TRY(ensure(&w.wsum, &w.wsum_elems, (size_t)NBMAX * (rup(n_local_max + NBMAX, 128) + 128)));
         TRY(ensure(&w.ypk, &w.ypk_elems, (size_t)(NBMAX / KC) * YT * LDK * ((n_local_max + YT - 1) / YT + 2)));
         TRY(ensure(&w.linv, &w.linv_elems, (size_t)NBMAX * NBMAX));
     }
-    for (int b = 0; b < 3; ++b)
-        if (!c->linv_ring[b]) { size_t o2 = 0; TRY(ensure(&c->linv_ring[b], &o2, (size_t)NBMAX * NBMAX)); }
     size_t one = 0;
     if (!c->sm_ticket) { CU(cudaMalloc((void**)&c->sm_ticket, sizeof(unsigned int) * 1024)); CU(cudaMemset(c->sm_ticket, 0, sizeof(unsigned int) * 1024)); }
     if (!c->cells2) {
@@ -742,6 +756,33 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             cudaStreamWaitEvent(s, evPanel[k], 0);
         }
     };
+    // Host entry (dhqr_qr_host_f64, one rank, first pass): columns [wend, lend) are still on their way to the device in chunks
+    // (c->up_chunks).  The schedule runs on the window [col0, wend); a chunk joins at the step its plan names - at the latest
+    // while it still lies right of panel k+2 - after a CATCH-UP on its own stream: the reflectors of panels < k, re-packed from
+    // the factored columns, applied to the chunk with the T' kept in the per-panel slots.  Same reflectors in the same order on
+    // every column, only the time at which a column receives them changes.
+    const bool windowed = !c->up_chunks.empty() && c->nranks == 1 && K0 == 0;
+    int64_t wend = windowed ? std::min(lend, c->up_chunks.front().c0) : lend;
+    size_t upnext = 0;
+    std::vector<char> haveTslot(K, 0);
+    cudaStream_t cu = c->cu_stream;
+    auto catch_up = [&](const dhqr_context::UpChunk& u, int k, cudaEvent_t done) -> int {
+        cudaStreamWaitEvent(cu, u.ev, 0);
+        for (int q = K0; q < k; ++q) {
+            const Panel& pq = panels[q];
+            const PanelGeom gq = panel_geom(pq, m);
+            cudaStreamWaitEvent(cu, evPanel[q], 0);                   // V_q is final in A ...
+            cudaStreamWaitEvent(cu, evNext[q], 0);                    // ... and T'_q sits in its slot
+            dim3 grid((unsigned)std::min<int64_t>((gq.vrows / 4 + 255) / 256, 4 * c->sms), gq.nbp <= IB ? IB : NBMAX);
+            k_pack<<<grid, 256, 0, cu>>>(A + (pq.c - col0) * lda + pq.c, lda, m - pq.c, pq.kb, 1, c->vpk2[3], 0, pq.c - gq.r0, gq.vrows);
+            TRY(post(c, cu, "k_pack"));
+            TRY(apply_block_reflector(c, cu, c->vpk2[3], c->ws[3], 0, gq.nbp, gq.rows, pq.c - gq.r0, A + (u.c0 - col0) * lda + gq.r0, lda,
+                                      (int)(u.c1 - u.c0), 0, haveTslot[q] != 0, c->tslot(q), q + 1));
+        }
+        cudaEventRecord(done, cu);
+        return 0;
+    };
+    std::vector<cudaEvent_t> evCatch;
     int rc = 0;
     cudaEvent_t fork = nullptr, hpdone = nullptr;
     do {
@@ -751,7 +792,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         std::vector<char> ownT(K, 0);       // T'_k already sits in the ring slot on this rank (wide panel factored here, k_trecon)
         if (c->rank == panels[K0].owner) {
             const bool wide = plan_wide(c, pl, panels, K0, m);
-            if ((rc = factor_outer_panel(c, hp, c->vpk2[K0 % 3], c->ws[1], panels[K0], m, col0, A, lda, alpha, K0, wide, c->linv_ring[K0 % 3]))) break;
+            if ((rc = factor_outer_panel(c, hp, c->vpk2[K0 % 3], c->ws[1], panels[K0], m, col0, A, lda, alpha, K0, wide, c->tslot(K0)))) break;
             if ((rc = mirror_panel_to_host(c, hp, panels[K0], m, col0, A, lda))) break;
             if (wide && c->wide_trecon) { ownT[K0] = 1; cudaEventRecord(evNext[K0], hp); }
         }
@@ -764,12 +805,29 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             const int64_t t1 = k + 1 < K ? panels[k + 1].c + panels[k + 1].kb : t0;      // end of panel k+1
             const int64_t t2 = k + 2 < K ? panels[k + 2].c + panels[k + 2].kb : t1;      // end of panel k+2
             int64_t lo, hi;
+            // chunks that join the window at this step: planned, or forced because step k+1 would reach into them
+            const int64_t wold = wend;
+            const size_t up0 = upnext;
+            if (windowed) {
+                const int64_t t3 = k + 3 < K ? panels[k + 3].c + panels[k + 3].kb : lend;   // end of panel k+3
+                while (upnext < c->up_chunks.size() && (c->up_chunks[upnext].join <= k || c->up_chunks[upnext].c0 < t3)) {
+                    const auto& u = c->up_chunks[upnext];
+                    if (u.c0 < t2 || u.c0 != wend) { rc = set_err(4005, "internal: upload chunk %d joins too late (step %d)", (int)upnext, k); break; }
+                    cudaEvent_t done;
+                    if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+                    evCatch.push_back(done);
+                    if ((rc = catch_up(u, k, done))) break;
+                    wend = u.c1;
+                    ++upnext;
+                }
+                if (rc) break;
+                if (wend < t2) { rc = set_err(4005, "internal: window ends at %lld before panel %d", (long long)wend, k + 2); break; }
+            }
             c->bulk_wide = (c->tail_cols <= 0) || (lend - t1 >= c->tail_cols);   // bulk-bound (wide) vs chain-bound (narrow) phase
-            double* lk = c->linv_ring[k % 3];
+            double* lk = c->tslot(k);
             bool haveT = ownT[k];                                        // T'_k in lk (this rank)
             if (k + 1 < K) {
-                // vpk[(k+1)%3] and linv_ring[(k+1)%3] were last read by the bulk update k-2 (and, on the owner of panel k-2,
-                // by its broadcast)
+                // vpk[(k+1)%3] was last read by the bulk update k-2 (and, on the owner of panel k-2, by its broadcast)
                 if (k - 2 >= K0) {
                     cudaStreamWaitEvent(hp, evBulk[k - 2], 0);
                     if (haveA2[k - 2]) cudaStreamWaitEvent(hp, evA2[k - 2], 0);
@@ -790,7 +848,7 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                     c->panel_ctas_hint = c->bulk_wide ? c->wide_panel_ctas : (c->tail_cols > 0 ? c->sms : c->wide_panel_ctas);
                     const bool widen = plan_wide(c, pl, panels, k + 1, m);
                     rc = factor_outer_panel(c, hp, c->vpk2[(k + 1) % 3], c->ws[1], panels[k + 1], m, col0, A, lda, alpha, k + 1, widen,
-                                            c->linv_ring[(k + 1) % 3]);
+                                            c->tslot(k + 1));
                     c->panel_ctas_hint = 0;
                     if (rc) break;
                     if (widen && c->wide_trecon) { ownT[k + 1] = 1; cudaEventRecord(evNext[k + 1], hp); }
@@ -819,11 +877,20 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             }
             if (!haveT) cudaEventRecord(evNext[k], hp);                  // keep the event defined (timeline tracing)
             wait_panel(st, k);
-            if (clip(t2, lend, lo, hi)) {
+            if (clip(t2, std::min(lend, wold), lo, hi)) {
                 if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);
                 if ((rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (lo - col0) * lda + g.r0, lda,
                                                 (int)(hi - lo), maxch, haveT, haveT ? lk : nullptr, k + 1))) break;
             }
+            for (size_t j = up0; j < upnext && !rc; ++j) {             // the chunks that joined at this step, each behind its catch-up
+                const auto& u = c->up_chunks[j];
+                cudaStreamWaitEvent(st, evCatch[j], 0);
+                if (haveT) cudaStreamWaitEvent(st, evNext[k], 0);
+                rc = apply_block_reflector(c, st, vk, c->ws[0], 0, g.nbp, g.rows, p.c - g.r0, A + (u.c0 - col0) * lda + g.r0, lda,
+                                           (int)(u.c1 - u.c0), maxch, haveT, haveT ? lk : nullptr, k + 1);
+            }
+            if (rc) break;
+            haveTslot[k] = haveT;
             cudaEventRecord(evBulk[k], st);
         }
         if (rc) break;
@@ -852,10 +919,13 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventRecord(hpdone, c->hp2_stream);
         cudaStreamWaitEvent(st, hpdone, 0);
+        cudaEventRecord(hpdone, cu);
+        cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventDestroy(hpdone);
     }
     for (cudaEvent_t e : evHp)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : evCatch) cudaEventDestroy(e);
     // events may be destroyed once recorded/waited on: the work they order is already enqueued
     if (fork) cudaEventDestroy(fork);
     for (int k = K0; k < K; ++k) { cudaEventDestroy(evPanel[k]); cudaEventDestroy(evNext[k]); cudaEventDestroy(evBulk[k]); cudaEventDestroy(evA2[k]); }
@@ -880,9 +950,9 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
     TRY(check_partition(col0s, nls, n));
     int64_t nlmax = 0;
     for (auto v : nls) nlmax = std::max(nlmax, v);
-    TRY(ensure_workspace(c, m, nlmax));
     std::vector<Panel> panels;
     build_panels(col0s, nls, nb, panels);
+    TRY(ensure_workspace(c, m, nlmax, (int64_t)panels.size(), !c->up_chunks.empty()));
     if (panels.empty()) return 0;
     // rank-uniform precondition, checked on every rank BEFORE the first collective: a panel that neither chain can take
     // would otherwise fail on its owner only and leave the other ranks inside ncclBroadcast
@@ -897,8 +967,14 @@ static int qr_blocked(dhqr_context* c, cudaStream_t st, int64_t m, int64_t n, in
         for (int k = pl.kstart; k < (int)panels.size(); ++k) any_wide |= plan_wide(c, pl, panels, k, m);
         k_wide_reset<<<1, 32, 0, st>>>(c->wctl);
         TRY(post(c, st, "k_wide_reset"));
-        const int rc = la && (int)panels.size() - pl.kstart > 1 ? qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels, pl)
-                                                                : qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels, pl);
+        const bool use_la = la && (int)panels.size() - pl.kstart > 1;
+        if (!use_la && !c->up_chunks.empty()) {   // the serial schedule knows nothing about columns still in flight: wait for them
+            for (const auto& u : c->up_chunks) CU(cudaStreamWaitEvent(st, u.ev, 0));
+            c->up_chunks.clear();
+        }
+        const int rc = use_la ? qr_blocked_lookahead(c, st, m, col0, nl, A, lda, alpha, panels, pl)
+                              : qr_blocked_serial(c, st, m, col0, nl, A, lda, alpha, panels, pl);
+        c->up_chunks.clear();                     // every chunk has joined (or the pass failed): a restart sees the whole matrix
         if (rc || !any_wide) return rc;
         // The wide chain is speculative: its guards are evaluated on the device.  One synchronisation per factorisation to
         // learn whether a panel was refused; if so, everything from that panel on was skipped on the device and is redone
@@ -1030,6 +1106,74 @@ static int apply_qt_local(dhqr_context* c, cudaStream_t st, int64_t m, int64_t c
     return 0;
 }
 
+// One right-hand side: T' of every local panel first (independent of b, so with several ranks every rank does this while b is
+// still with its predecessors), then the sweep with two GEMV-shaped launches per panel (k_qt_dot, k_qt_axpy).
+static constexpr int QT_MAXG = 1024;
+static int qt_prepare(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, const double* A, int64_t lda) {
+    const int npl = (int)((nl + NBMAX - 1) / NBMAX);
+    if (npl <= 0) return 0;
+    TRY(ensure(&c->qt_T, &c->qt_T_elems, (size_t)npl * NBMAX * NBMAX));
+    if (!c->qt_part) {
+        CU(cudaMalloc((void**)&c->qt_part, sizeof(double) * (size_t)(QT_MAXG + 1) * WP));     // last row: y
+        CU(cudaMalloc((void**)&c->qt_ticket, sizeof(unsigned int)));
+        CU(cudaMemset(c->qt_ticket, 0, sizeof(unsigned int)));
+    }
+    auto& w = c->ws[0];
+    if ((size_t)npl * NBMAX * NBMAX > w.wsum_elems) return set_err(4006, "internal: Gram workspace too small");
+    const int tiles = WP / G1_BN;
+    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
+    for (int p = 0; p < npl; ++p) {
+        const int64_t o = (int64_t)p * NBMAX, cs = col0 + o, r0 = cs & ~(int64_t)31;
+        const int kb = (int)std::min<int64_t>(NBMAX, nl - o);
+        const int64_t rows = m - r0, vrows = rup(rows, 128);
+        dim3 grid((unsigned)std::min<int64_t>((vrows / 4 + 255) / 256, 4 * c->sms), NBMAX);
+        pre(c, st);
+        k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk2[0], 0, cs - r0, vrows);
+        TRY(post(c, st, "k_pack"));
+        const int nchunks = (int)((rows + KC1 - 1) / KC1);
+        const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
+        GemmVtaArgs g1;
+        g1.vpk = c->vpk2[0]; g1.voff = 0; g1.nv = WP; g1.A = c->vpk2[0]; g1.lda = 2; g1.rows = rows; g1.na = 0; g1.nchunks = nchunks;
+        g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
+        pre(c, st);
+        K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
+        TRY(post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP));
+        pre(c, st);
+        k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum + (size_t)p * WP * WP);
+        TRY(post(c, st, "k_wreduce"));
+    }
+    pre(c, st);
+    k_tinv<128><<<npl, 512, smem_tinv(128), st>>>(w.wsum, c->qt_T, (int64_t)WP * WP);
+    TRY(post(c, st, "k_tinv128"));
+    return 0;
+}
+
+static int apply_qt_local_vec(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0, int64_t nl, const double* A, int64_t lda,
+                              double* b, int notrans) {
+    const int npl = (int)((nl + NBMAX - 1) / NBMAX);
+    for (int q = 0; q < npl; ++q) {
+        const int p = notrans ? npl - 1 - q : q;
+        const int64_t o = (int64_t)p * NBMAX, cs = col0 + o;
+        QtArgs a;
+        a.V = A + o * lda + cs; a.lda = lda; a.mp = m - cs; a.kb = (int)std::min<int64_t>(NBMAX, nl - o);
+        a.b = b + cs; a.Linv = c->qt_T + (size_t)p * NBMAX * NBMAX;
+        a.part = c->qt_part; a.y = c->qt_part + (size_t)QT_MAXG * WP; a.ticket = c->qt_ticket; a.trans = notrans;
+        int64_t rpc = rup(std::max<int64_t>((a.mp + 2 * c->sms - 1) / (2 * c->sms), 32), 32);     // two CTAs per SM
+        rpc = std::min<int64_t>(rpc, QT_MAXROWS);
+        const int64_t G = (a.mp + rpc - 1) / rpc;
+        if (G > QT_MAXG) return set_err(4007, "internal: too many k_qt_dot CTAs");                  // callers check m first
+        a.rows_per_cta = (int)rpc;
+        pre(c, st);
+        k_qt_dot<<<(unsigned)G, QT_THREADS, 0, st>>>(a);
+        TRY(post(c, st, "k_qt_dot", 8.0 * (double)a.mp * a.kb));
+        pre(c, st);
+        k_qt_axpy<<<(unsigned)((a.mp + QT_THREADS - 1) / QT_THREADS), QT_THREADS, 0, st>>>(a);
+        TRY(post(c, st, "k_qt_axpy", 8.0 * (double)a.mp * a.kb));
+    }
+    return 0;
+}
+static bool qt_vec_ok(const dhqr_context* c, int64_t m, int nrhs) { return c->qt_vec && nrhs == 1 && m <= (int64_t)QT_MAXG * QT_MAXROWS; }
+
 static int backsolve_local(dhqr_context* c, cudaStream_t st, int64_t col0, int64_t nl, const double* A, int64_t lda,
                            const double* alpha, double* y, int64_t ldy, int nrhs, double* x, int64_t ldx) {
     if (nl <= 0) return 0;
@@ -1082,6 +1226,7 @@ static int create_common(dhqr_handle* h, int device) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->cu_stream, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1130,13 +1275,13 @@ int dhqr_destroy(dhqr_handle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    cudaFree(c->vpk2[2]);
-    for (int b = 0; b < 3; ++b) cudaFree(c->linv_ring[b]);
-    for (int b = 0; b < 3; ++b) {
-        if (b < 2) cudaFree(c->vpk2[b]);
+    cudaFree(c->linv_all);
+    for (int b = 0; b < 4; ++b) {
+        cudaFree(c->vpk2[b]);
         cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
     cudaFree(c->uw_flags);
+    cudaFree(c->qt_T); cudaFree(c->qt_part); cudaFree(c->qt_ticket);
     cudaFree(c->wctl); cudaFree(c->wbuf); cudaFree(c->wstamps); cudaFree(c->bs_cells);
     cudaFree(c->cells); cudaFree(c->cells2); cudaFree(c->fast_stats); cudaFree(c->panel_trace); cudaFree(c->sm_ticket);
     if (c->hp_hi) cudaStreamDestroy(c->hp_hi);
@@ -1150,6 +1295,7 @@ int dhqr_destroy(dhqr_handle c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->cu_stream) cudaStreamDestroy(c->cu_stream);
     delete c;
     return 0;
 }
@@ -1186,6 +1332,17 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
         c->wide_trecon = value ? 1 : 0;
     } else if (!strcmp(key, "host_trace")) {
         c->host_trace = value ? 1 : 0;
+    } else if (!strcmp(key, "host_chunk")) {
+        if (value < 0 || value % 128) return set_err(-3, "host_chunk must be a non-negative multiple of 128");
+        c->host_chunk = (int)value;
+    } else if (!strcmp(key, "host_h2d_gbs")) {
+        if (value < 1) return set_err(-3, "host_h2d_gbs < 1");
+        c->host_h2d_gbs = (int)value;
+    } else if (!strcmp(key, "host_tflops")) {
+        if (value < 1) return set_err(-3, "host_tflops < 1");
+        c->host_tflops = (int)value;
+    } else if (!strcmp(key, "qt_vec")) {
+        c->qt_vec = value ? 1 : 0;
     } else if (!strcmp(key, "hp2")) {
         c->hp2 = value ? 1 : 0;
     } else if (!strcmp(key, "bs_wave")) {
@@ -1327,8 +1484,11 @@ int dhqr_apply_qt_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, 
     TRY(ensure_workspace(c, m, std::max<int64_t>(n_local, nrhs)));
     // C3 (S:227-229): owners act on b one after the other; b travels rank -> rank
     const size_t cnt = (size_t)ldb * (nrhs - 1) + m;
+    const bool vec = qt_vec_ok(c, m, nrhs);
+    if (vec) TRY(qt_prepare(c, st, m, col0, n_local, dA, lda));
     if (c->nranks > 1 && c->rank > 0) NC(g_nccl.Recv(d_b, cnt, ncclFloat64, c->rank - 1, c->comm, st));
-    TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs));
+    if (vec) TRY(apply_qt_local_vec(c, st, m, col0, n_local, dA, lda, d_b, 0));
+    else TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs));
     if (c->nranks > 1) {
         if (c->rank + 1 < c->nranks) NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
         NC(g_nccl.Broadcast(d_b, d_b, cnt, ncclFloat64, c->nranks - 1, c->comm, st));
@@ -1351,8 +1511,11 @@ int dhqr_apply_q_f64(dhqr_handle c, int64_t m, int64_t n_global, int64_t col0, i
     TRY(ensure_workspace(c, m, std::max<int64_t>(n_local, nrhs)));
     // b <- H_1 ... H_n b: the owners act in reverse rank order, b travels rank -> rank - 1
     const size_t cnt = (size_t)ldb * (nrhs - 1) + m;
+    const bool vec = qt_vec_ok(c, m, nrhs);
+    if (vec) TRY(qt_prepare(c, st, m, col0, n_local, dA, lda));
     if (c->nranks > 1 && c->rank + 1 < c->nranks) NC(g_nccl.Recv(d_b, cnt, ncclFloat64, c->rank + 1, c->comm, st));
-    TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs, 1));
+    if (vec) TRY(apply_qt_local_vec(c, st, m, col0, n_local, dA, lda, d_b, 1));
+    else TRY(apply_qt_local(c, st, m, col0, n_local, dA, lda, d_b, ldb, nrhs, 1));
     if (c->nranks > 1) {
         if (c->rank > 0) NC(g_nccl.Send(d_b, cnt, ncclFloat64, c->rank - 1, c->comm, st));
         NC(g_nccl.Broadcast(d_b, d_b, cnt, ncclFloat64, 0, c->comm, st));
@@ -1527,25 +1690,64 @@ int dhqr_partialdot_c64(dhqr_handle c, const void* d_a, const void* d_b, int64_t
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------
+// Plan of the chunked upload of dhqr_qr_host_f64: chunk boundaries B (multiples of nb; B[0] = 0, B.back() = n) and, for every
+// chunk after the first, the step of the look-ahead schedule at which it joins the trailing matrix.  A chunk joins as soon as
+// the model says it has arrived (earlier = less catch-up work), at the latest one step before the panel chain reaches into it.
+// The model has two parameters (options host_h2d_gbs, host_tflops); a wrong guess costs idle time, never correctness: the
+// driver orders every use of a chunk behind its upload event and forces a join that the plan names too late.
+static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std::vector<int64_t>& B, std::vector<int>& join) {
+    B.assign(1, 0);
+    join.assign(1, 0);
+    const int64_t chunk = rup(c->host_chunk, nb), first = std::max(rup(chunk + chunk / 2, nb), 3 * (int64_t)nb);   // the schedule starts on panels 0..2
+    if (c->host_chunk <= 0 || m < n || n < first + chunk) { B.push_back(n); return; }
+    B.push_back(first);
+    while (B.back() < n) B.push_back(std::min(n, B.back() + chunk));
+    if (n - B[B.size() - 2] < chunk / 2) B.erase(B.end() - 2);           // no sliver at the end
+    const int nch = (int)B.size() - 1, K = (int)((n + nb - 1) / nb);
+    const double U = 1e9 * c->host_h2d_gbs, R = 1e12 * c->host_tflops, chain = 0.3e-3;
+    auto tup = [&](int j) { return (double)B[j + 1] * (double)m * 8.0 / U; };
+    join.assign(nch, 0);
+    double T = tup(0);
+    int64_t wend = B[1];
+    int nxt = 1;
+    for (int k = 0; k < K; ++k) {
+        while (nxt < nch && (B[nxt] < std::min<int64_t>(n, (int64_t)nb * (k + 4)) || tup(nxt) <= T)) {
+            T = std::max(T, tup(nxt));
+            for (int q = 0; q < k; ++q) T += 4.0 * (double)(m - (int64_t)nb * q) * nb * (double)(B[nxt + 1] - B[nxt]) / R;   // catch-up
+            join[nxt] = k;
+            wend = B[nxt + 1];
+            ++nxt;
+        }
+        T += std::max(chain, 4.0 * (double)(m - (int64_t)nb * k) * nb * (double)std::max<int64_t>(0, wend - (int64_t)nb * (k + 1)) / R);
+    }
+}
+
 int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t lda, double* h_alpha, int nb) {
     TRY(check_common(c, m, n, 0, n, hA, lda));
     if (n > 0 && !h_alpha) return set_err(-6, "null alpha");
     if (c->nranks != 1) return set_err(-1, "host entry points are single-GPU");
+    if (nb != 0 && nb != 1 && (nb < 32 || nb > 128 || nb % 32)) return set_err(-9, "nb must be 0, 1 or a multiple of 32 in [32,128]");
     if (n == 0) return 0;
     CU(cudaSetDevice(c->device));
     const int64_t ldd = rup(m, 32);                       // padded device leading dimension (aligned TMA sources)
+    const bool blocked = (nb != 1);
+    const int nbe = nb == 0 ? c->nb : nb;
+    // The matrix goes up in column chunks.  Only the first upload is exposed: the factorisation starts on it, every later chunk
+    // travels while the device works and joins the trailing matrix through a catch-up (qr_blocked_lookahead); finished panels
+    // stream back while later panels are factored.  One factorisation, the same reflectors as with the matrix resident.
+    std::vector<int64_t> B;
+    std::vector<int> join;
+    if (blocked) plan_upload(c, m, n, nbe, B, join);
+    else { B = {0, n}; join = {0}; }
+    const int nch = (int)B.size() - 1;
     TRY(ensure(&c->hostA, &c->hostA_elems, (size_t)ldd * n + (size_t)n));
-    TRY(ensure_workspace(c, m, n));       // once, for the full width: growing it between the two halves would synchronise the device
+    // everything sized once, before the pipeline starts: growing a buffer later would synchronise the device
+    TRY(ensure_workspace(c, m, n, blocked ? (n + nbe - 1) / nbe + 1 : 0, nch > 1));
     double* dA = c->hostA;
     double* dal = c->hostA + (size_t)ldd * n;
     cudaStream_t st = c->copy_stream;
-    const bool blocked = (nb != 1);
-    const int nbe = nb == 0 ? c->nb : nb;
-    // two column halves when the matrix is big enough: the right half uploads while the left half is factored,
-    // then Q_left' is applied to it and the remainder is factored (same reflectors, same flops)
-    const int64_t ns = (blocked && n >= 2048 && m >= n) ? rup(n / 2, nbe) : n;
     int rc = 0;
-    cudaEvent_t evUp = nullptr, evR12 = nullptr;
+    std::vector<cudaEvent_t> evUp;
     struct timespec ts0;
     clock_gettime(CLOCK_MONOTONIC, &ts0);
     auto stamp = [&](const char* what, bool sync_all) {
@@ -1555,56 +1757,56 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
         clock_gettime(CLOCK_MONOTONIC, &ts);
         fprintf(stderr, "[dhqr host] %-34s %8.2f ms\n", what, (ts.tv_sec - ts0.tv_sec) * 1e3 + (ts.tv_nsec - ts0.tv_nsec) * 1e-6);
     };
+    if (c->host_trace) {
+        fprintf(stderr, "[dhqr host] upload chunks (first column : join step):");
+        for (int j = 0; j < nch; ++j) fprintf(stderr, " %lld:%d", (long long)B[j], join[j]);
+        fprintf(stderr, "\n");
+    }
+    c->up_chunks.clear();
     do {
-        if (cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)ns, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
-        stamp("left half uploaded", true);
-        if (ns < n) {
-            cudaEventCreateWithFlags(&evUp, cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&evR12, cudaEventDisableTiming);
-            // the right half goes up AFTER the left half (two concurrent uploads would share the link and delay the start of
-            // the factorisation by half an upload), on its own stream so that it overlaps the factorisation of the left half
-            cudaEventRecord(evUp, st);
-            cudaStreamWaitEvent(c->h2d_stream, evUp, 0);
-            if (cudaMemcpy2DAsync(dA + ns * ldd, (size_t)ldd * 8, hA + ns * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(n - ns),
-                                  cudaMemcpyHostToDevice, c->h2d_stream) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
-            cudaEventRecord(evUp, c->h2d_stream);
+        if (cudaMemcpy2DAsync(dA, (size_t)ldd * 8, hA, (size_t)lda * 8, (size_t)m * 8, (size_t)B[1], cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
+        if (nch > 1) {
+            // the later chunks go up one after the other BEHIND the first (concurrent uploads would share the link and delay the
+            // start of the factorisation), on their own stream
+            cudaEvent_t e0;
+            if (cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+            evUp.push_back(e0);
+            cudaEventRecord(e0, st);
+            cudaStreamWaitEvent(c->h2d_stream, e0, 0);
+            for (int j = 1; j < nch && !rc; ++j) {
+                cudaEvent_t e;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+                evUp.push_back(e);
+                if (cudaMemcpy2DAsync(dA + B[j] * ldd, (size_t)ldd * 8, hA + B[j] * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(B[j + 1] - B[j]),
+                                      cudaMemcpyHostToDevice, c->h2d_stream) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
+                cudaEventRecord(e, c->h2d_stream);
+                c->up_chunks.push_back({B[j], B[j + 1], e, join[j]});
+            }
+            if (rc) break;
         }
+        stamp("first chunk uploaded", true);
         if (blocked) { c->mirror_host = hA; c->mirror_lda = lda; }   // finished panels stream back while later panels are factored
-        rc = dhqr_qr_f64(c, m, ns, 0, ns, dA, ldd, dal, nb, st);
+        rc = dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st);
         c->mirror_host = nullptr;
         if (rc) break;
-        stamp("left half factored", true);
-        if (ns < n) {
-            cudaStreamWaitEvent(st, evUp, 0);
-            stamp("right half uploaded", true);
-            if ((rc = ensure_workspace(c, m, n))) break;
-            if ((rc = apply_qt_local(c, st, m, 0, ns, dA, ldd, dA + ns * ldd, ldd, (int)(n - ns)))) break;   // right half <- Q_left' * right half
-            cudaEventRecord(evR12, st);
-            cudaStreamWaitEvent(c->d2h_stream, evR12, 0);                                                    // R12 is final
-            if (cudaMemcpy2DAsync(hA + ns * lda, (size_t)lda * 8, dA + ns * ldd, (size_t)ldd * 8, (size_t)ns * 8, (size_t)(n - ns),
-                                  cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
-            c->mirror_host = hA + ns * lda + ns; c->mirror_lda = lda;
-            stamp("right half <- Q_left' (enqueued+sync)", true);
-            rc = dhqr_qr_f64(c, m - ns, n - ns, 0, n - ns, dA + ns * ldd + ns, ldd, dal + ns, nb, st);
-            c->mirror_host = nullptr;
-            if (rc) break;
-            stamp("right part factored", true);
-        }
+        stamp("factored", true);
         if (!blocked)
             if (cudaMemcpy2DAsync(hA, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
         if (cudaMemcpyAsync(h_alpha, dal, (size_t)n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = set_err(1001, "D2H failed"); break; }
     } while (0);
     c->mirror_host = nullptr;
+    c->up_chunks.clear();
     cudaError_t e0 = cudaStreamSynchronize(c->h2d_stream), e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
+    cudaError_t e3 = cudaStreamSynchronize(c->cu_stream);
     stamp("everything back on the host", false);
     for (cudaEvent_t ev : c->panel_events) cudaEventDestroy(ev);
     c->panel_events.clear();
-    if (evUp) cudaEventDestroy(evUp);
-    if (evR12) cudaEventDestroy(evR12);
+    for (cudaEvent_t ev : evUp) cudaEventDestroy(ev);
     if (rc) return rc;
     if (e0 != cudaSuccess) return set_err(1000 + (int)e0, "qr_host H2D: %s", cudaGetErrorString(e0));
     if (e1 != cudaSuccess) return set_err(1000 + (int)e1, "qr_host: %s", cudaGetErrorString(e1));
     if (e2 != cudaSuccess) return set_err(1000 + (int)e2, "qr_host D2H: %s", cudaGetErrorString(e2));
+    if (e3 != cudaSuccess) return set_err(1000 + (int)e3, "qr_host catch-up: %s", cudaGetErrorString(e3));
     return 0;
 }
 

@@ -748,10 +748,13 @@ __device__ __forceinline__ void tinv_core(double* L, double* T, int tid, int nth
     }
 }
 
+// grid.x > 1: a batch, CTA g inverts the block at Ws + g * ws_stride into Linv + g * NBP * NBP
 template <int NBP>
-__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv) {
+__global__ void __launch_bounds__(512, 1) k_tinv(const double* __restrict__ Ws, double* __restrict__ Linv, int64_t ws_stride = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
+    Ws += (int64_t)blockIdx.x * ws_stride;
+    Linv += (int64_t)blockIdx.x * NBP * NBP;
     if (NBP == WP) {
         // (I + stril(S))^{-1} = ((I + striu(S'))^{-1})': row r of U = I + striu(S') is column r of S below the diagonal, i.e. a
         // contiguous run of Ws, and row j of U^{-1} is column j of the result: both transfers are linear in memory
@@ -1550,6 +1553,111 @@ __global__ void k_pack(const double* __restrict__ A, int64_t lda, int64_t mp, in
         *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
     }
 }
+// ------------------------------------------------------------------------------------------------
+// Q'b / Qb with ONE right-hand side (S:226-242).  The sweep over the panels is sequential, but once T' of every panel is
+// known (b-independent: packed Gram matrices + a batched k_tinv before the sweep) a panel costs two GEMV-shaped passes over
+// its reflectors, read IN PLACE from the factored matrix (lower trapezoid including the diagonal, S:232-242):
+//   k_qt_dot : w = V'b, one partial per CTA (16 independent column accumulators per lane = S:42-49 for 16 columns at once,
+//              warp-shuffle reduction); the CTA that arrives last sums the partials in CTA order (deterministic) and forms
+//              y = -T'w (Q'b) or y = -Tw (Qb)
+//   k_qt_axpy: b += V y   (S:156-160 for the whole panel; V comes from L2, the first pass just read it)
+// ------------------------------------------------------------------------------------------------
+constexpr int QT_THREADS = 256;
+constexpr int QT_MAXROWS = 512;            // rows of b a k_qt_dot CTA keeps in shared memory
+struct QtArgs {
+    const double* V;        // first column of the panel at its pivot row
+    int64_t lda;
+    int64_t mp;             // rows from the pivot row to the end
+    int kb;                 // reflectors in the panel (<= 128)
+    double* b;              // right-hand side at the pivot row
+    const double* Linv;     // T' of the panel: 128 x 128, element (i, k) at k * 128 + i, lower triangular
+    double* part;           // [gridDim.x][128]
+    double* y;              // [128]
+    unsigned int* ticket;   // zero on entry, zero again on exit
+    int rows_per_cta;       // multiple of 32, <= QT_MAXROWS
+    int trans;
+};
+
+__global__ void __launch_bounds__(QT_THREADS, 2) k_qt_dot(QtArgs a) {
+    __shared__ double sb[QT_MAXROWS];
+    __shared__ double sw[WP];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - r0));
+    for (int r = tid; r < nr; r += QT_THREADS) sb[r] = a.b[r0 + r];
+    __syncthreads();
+    // warp w owns columns 16 w .. 16 w + 15; rows r0 + lane + 32 i
+    const int c0 = warp * 16;
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    if (c0 < a.kb) {
+        const double* v = a.V + (int64_t)c0 * a.lda + r0;
+        const bool full = (c0 + 16 <= a.kb) && (r0 >= c0 + 15);     // every column live, every row below the diagonal
+        for (int r = lane; r < nr; r += 32) {
+            const double bv = sb[r];
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += v[(int64_t)j * a.lda + r] * bv;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < a.kb && r0 + r >= c0 + j) acc[j] += v[(int64_t)j * a.lda + r] * bv;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a.part[(int64_t)blockIdx.x * WP + c0 + j] = acc[j];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < WP) {
+        double s = 0.0;
+        for (unsigned g = 0; g < gridDim.x; ++g) s += __ldcg(&a.part[(int64_t)g * WP + tid]);
+        sw[tid] = s;
+    }
+    __syncthreads();
+    if (tid < WP) {
+        const int i = tid;
+        double s = 0.0;
+        if (!a.trans) for (int k = 0; k <= i; ++k) s += a.Linv[k * WP + i] * sw[k];       // y = -T' w
+        else for (int k = i; k < WP; ++k) s += a.Linv[i * WP + k] * sw[k];                 // y = -T w
+        a.y[i] = -s;
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_qt_axpy(QtArgs a) {
+    __shared__ double sy[WP];
+    const int tid = threadIdx.x;
+    if (tid < WP) sy[tid] = a.y[tid];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * QT_THREADS + tid;
+    if (r >= a.mp) return;
+    const int nc = (int)min((int64_t)a.kb, r + 1);            // columns with row r at or below their diagonal
+    const double* v = a.V + r;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 0;
+    for (; c + 8 <= nc; c += 8) {
+        const double v0 = v[(int64_t)c * a.lda], v1 = v[(int64_t)(c + 1) * a.lda], v2 = v[(int64_t)(c + 2) * a.lda], v3 = v[(int64_t)(c + 3) * a.lda];
+        const double v4 = v[(int64_t)(c + 4) * a.lda], v5 = v[(int64_t)(c + 5) * a.lda], v6 = v[(int64_t)(c + 6) * a.lda], v7 = v[(int64_t)(c + 7) * a.lda];
+        s0 += v0 * sy[c] + v4 * sy[c + 4];
+        s1 += v1 * sy[c + 1] + v5 * sy[c + 5];
+        s2 += v2 * sy[c + 2] + v6 * sy[c + 6];
+        s3 += v3 * sy[c + 3] + v7 * sy[c + 7];
+    }
+    for (; c < nc; ++c) s0 += v[(int64_t)c * a.lda] * sy[c];
+    a.b[r] += (s0 + s1) + (s2 + s3);
+}
+
 // zero packed columns [c0, c1) over all chunks
 __global__ void k_vpk_zero_cols(double* __restrict__ vpk, int64_t nchunks, int c0, int c1) {
     const int64_t per = (int64_t)(c1 - c0) * LD1;
