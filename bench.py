@@ -388,6 +388,14 @@ def run_ours(args):
                         "launches": prof[dom]["count"], "avg_launch_ms": prof[dom]["ms"] / max(1, prof[dom]["count"]),
                         "share_of_step": prof[dom]["ms"] / tot if tot else None,
                         "whole_qr_frac_of_peak": value / 1e3 / peak / world, "classes": classes}
+                # what the library itself reaches at the two bulk shapes of step 0 (K = nb = 128 for C += V Y; a 128-row output for
+                # W = V'C): a comparator for the shape, not a roofline denominator
+                try:
+                    roof["cublas_same_shape"] = cublas_bulk_shapes(torch, dev, m, max(nl - 3 * (nb or 128), 128), nb or 128)
+                    roof["cublas_same_shape"]["note"] = ("cuBLAS DGEMM (torch fp64 addmm / mm) at the shapes of the step-0 bulk update; "
+                                                         "k_gemm_cvy128 / k_gemm_vta128 averages above are over all 31 launches of the sweep")
+                except Exception as ex:   # a comparator only: never fail the bench line on it
+                    roof["cublas_same_shape"] = {"error": str(ex)[:200]}
 
     # ---- e2e: host buffers through the reference-facing entry ----
     e2e = None
@@ -493,6 +501,30 @@ def dgemm_peak(torch, dev, nn=8192):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return 2.0 * nn ** 3 / (best * 1e-3) / 1e12
+
+
+def cublas_bulk_shapes(torch, dev, rows, ncols, nb):
+    """TFLOP/s of cuBLAS DGEMM at the two bulk-update shapes: C(rows x ncols) += V(rows x nb) Y(nb x ncols) and W(nb x ncols) = V'C."""
+    V = torch.rand(nb, rows, dtype=torch.float64, device=dev)       # = V' row-major, i.e. V column-major
+    Y = torch.rand(ncols, nb, dtype=torch.float64, device=dev)      # = Y' row-major
+    Ct = torch.rand(ncols, rows, dtype=torch.float64, device=dev)   # = C' row-major, i.e. C column-major
+
+    def best_ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    fl = 2.0 * rows * ncols * nb
+    t_cvy = best_ms(lambda: torch.addmm(Ct, Y, V, out=Ct))           # C' += Y'V'  (K = nb)
+    t_vta = best_ms(lambda: torch.mm(V, Ct.t()))                      # W = V'C     (K = rows)
+    return {"rows": rows, "ncols": ncols, "k": nb, "cvy_tflops": fl / (t_cvy * 1e-3) / 1e12, "vta_tflops": fl / (t_vta * 1e-3) / 1e12}
 
 
 def main():

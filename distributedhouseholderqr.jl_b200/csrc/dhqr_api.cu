@@ -109,13 +109,13 @@ struct dhqr_context {
     // workspace
     // three V buffers (panels k, k+1 and the one being broadcast live at the same time under look-ahead) and two
     // workspace sets (set 0: trailing update on the caller's stream; set 1: panel chain on the high-priority stream)
-    double* vpk2[4] = {nullptr, nullptr, nullptr, nullptr}; size_t vpk_elems[4] = {0, 0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]; [3]: catch-up of late column chunks (host entry)
+    double* vpk2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t vpk_elems[6] = {0, 0, 0, 0, 0, 0}; int64_t vrows_cap = 0;   // packed V [chunk][128][68]; [3..5]: catch-up of late column chunks (host entry)
     struct WSet {
         double* wpart = nullptr; size_t wpart_elems = 0;                // gemm_vta partials
         double* wsum = nullptr;  size_t wsum_elems = 0;                 // reduced Wext
         double* ypk = nullptr;   size_t ypk_elems = 0;                  // packed Y = -T'W
         double* linv = nullptr;  size_t linv_elems = 0;                 // [128*128]
-    } ws[4];                                                            // [2]: the chain's second apply (columns of panel k+2) on its own stream; [3]: catch-up (host entry)
+    } ws[6];                                                            // [2]: the chain's second apply (columns of panel k+2) on its own stream; [3..5]: catch-up (host entry)
     double* linv_all = nullptr; size_t linv_all_elems = 0;              // T' of every outer panel of the factorisation in flight (look-ahead): slot k = panel k
     double* tslot(int k) const { return linv_all + (size_t)k * 128 * 128; }
     cudaStream_t hp_stream = nullptr;                                   // stream of the panel chain (high priority by default)
@@ -175,13 +175,15 @@ struct dhqr_context {
     cudaStream_t copy_stream = nullptr;      // compute stream of the _host_ entry points
     cudaStream_t d2h_stream = nullptr;       // drains finished panels to the host while the factorisation continues
     cudaStream_t h2d_stream = nullptr;       // uploads the later column chunks while the first ones are being factored
-    cudaStream_t cu_stream = nullptr;        // catch-up: reflectors of finished panels applied to a column chunk that arrived late
+    cudaStream_t cu_stream[3] = {nullptr, nullptr, nullptr};   // catch-up: reflectors of finished panels applied to a column chunk that arrived late (chunks alternate)
     // dhqr_qr_host_f64 -> look-ahead driver: column chunks still on their way to the device.  Chunk j = global columns [c0, c1),
     // usable once `ev` has fired, joins the trailing matrix at step `join` (after a catch-up with the reflectors of panels < join)
     struct UpChunk { int64_t c0, c1; cudaEvent_t ev; int join; };
     std::vector<UpChunk> up_chunks;
     int host_chunk = 512;                    // option: columns per upload chunk (0: one upload, no overlap)
     int host_h2d_gbs = 50, host_tflops = 27; // option: what the join-step planner assumes about the link and the device
+    int host_chain_us = 300;                 // option: ... and about the duration of a step of the schedule while the window is narrow
+    int host_cu_streams = 2;                 // option: catch-up streams in use (1..3)
     std::vector<cudaEvent_t> panel_events;
     // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
     double* mirror_host = nullptr;
@@ -267,10 +269,10 @@ static int ensure_workspace(dhqr_context* c, int64_t m, int64_t n_local_max, int
         for (int b = 0; b < 3; ++b) TRY(ensure(&c->vpk2[b], &c->vpk_elems[b], (size_t)(vrows / KC1) * VPK_CHUNK));
         c->vrows_cap = vrows;
     }
-    if (catchup) TRY(ensure(&c->vpk2[3], &c->vpk_elems[3], (size_t)(vrows / KC1) * VPK_CHUNK));
+    if (catchup) for (int b = 3; b < 3 + c->host_cu_streams; ++b) TRY(ensure(&c->vpk2[b], &c->vpk_elems[b], (size_t)(vrows / KC1) * VPK_CHUNK));
     TRY(ensure(&c->linv_all, &c->linv_all_elems, (size_t)std::max<int64_t>(npanels, 4) * NBMAX * NBMAX));
     const int64_t tiles_max = (n_local_max + NBMAX + G1_BN - 1) / G1_BN + 1;
-    for (int b = 0; b < (catchup ? 4 : 3); ++b) {
+    for (int b = 0; b < (catchup ? 3 + c->host_cu_streams : 3); ++b) {
         auto& w = c->ws[b];
         // set 2 only ever updates the <= 128 columns of one panel: a quarter of the split-K partial buffer is plenty
         TRY(ensure(&w.wpart, &w.wpart_elems, (size_t)(b != 2 ? std::max(WPART_TILES, tiles_max) : WPART_TILES / 4) * NBMAX * G1_BN));
@@ -765,8 +767,10 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
     int64_t wend = windowed ? std::min(lend, c->up_chunks.front().c0) : lend;
     size_t upnext = 0;
     std::vector<char> haveTslot(K, 0);
-    cudaStream_t cu = c->cu_stream;
-    auto catch_up = [&](const dhqr_context::UpChunk& u, int k, cudaEvent_t done) -> int {
+    auto catch_up = [&](const dhqr_context::UpChunk& u, int lane, int k, cudaEvent_t done) -> int {
+        cudaStream_t cu = c->cu_stream[lane];
+        double* vpk_cu = c->vpk2[3 + lane];
+        auto& ws_cu = c->ws[3 + lane];
         cudaStreamWaitEvent(cu, u.ev, 0);
         for (int q = K0; q < k; ++q) {
             const Panel& pq = panels[q];
@@ -774,15 +778,16 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
             cudaStreamWaitEvent(cu, evPanel[q], 0);                   // V_q is final in A ...
             cudaStreamWaitEvent(cu, evNext[q], 0);                    // ... and T'_q sits in its slot
             dim3 grid((unsigned)std::min<int64_t>((gq.vrows / 4 + 255) / 256, 4 * c->sms), gq.nbp <= IB ? IB : NBMAX);
-            k_pack<<<grid, 256, 0, cu>>>(A + (pq.c - col0) * lda + pq.c, lda, m - pq.c, pq.kb, 1, c->vpk2[3], 0, pq.c - gq.r0, gq.vrows);
+            k_pack<<<grid, 256, 0, cu>>>(A + (pq.c - col0) * lda + pq.c, lda, m - pq.c, pq.kb, 1, vpk_cu, 0, pq.c - gq.r0, gq.vrows);
             TRY(post(c, cu, "k_pack"));
-            TRY(apply_block_reflector(c, cu, c->vpk2[3], c->ws[3], 0, gq.nbp, gq.rows, pq.c - gq.r0, A + (u.c0 - col0) * lda + gq.r0, lda,
+            TRY(apply_block_reflector(c, cu, vpk_cu, ws_cu, 0, gq.nbp, gq.rows, pq.c - gq.r0, A + (u.c0 - col0) * lda + gq.r0, lda,
                                       (int)(u.c1 - u.c0), 0, haveTslot[q] != 0, c->tslot(q), q + 1));
         }
         cudaEventRecord(done, cu);
         return 0;
     };
     std::vector<cudaEvent_t> evCatch;
+    std::vector<int> joinedAt;
     int rc = 0;
     cudaEvent_t fork = nullptr, hpdone = nullptr;
     do {
@@ -814,9 +819,10 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                     const auto& u = c->up_chunks[upnext];
                     if (u.c0 < t2 || u.c0 != wend) { rc = set_err(4005, "internal: upload chunk %d joins too late (step %d)", (int)upnext, k); break; }
                     cudaEvent_t done;
-                    if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+                    if (cudaEventCreateWithFlags(&done, evflags) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
                     evCatch.push_back(done);
-                    if ((rc = catch_up(u, k, done))) break;
+                    joinedAt.push_back(k);
+                    if ((rc = catch_up(u, (int)(upnext % (size_t)c->host_cu_streams), k, done))) break;
                     wend = u.c1;
                     ++upnext;
                 }
@@ -909,6 +915,19 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
                 cudaEventElapsedTime(&c->la_times[3 * k + 1], fork, evNext[k]);
                 cudaEventElapsedTime(&c->la_times[3 * k + 2], fork, evBulk[k]);
             }
+            if (c->host_trace) {   // stage timeline of the pipelined host entry (ms since the first chunk was on the device)
+                for (size_t j = 0; j < evCatch.size(); ++j) {
+                    float tu = -1.f, tc = -1.f;
+                    cudaEventSynchronize(evCatch[j]);
+                    cudaEventElapsedTime(&tu, fork, c->up_chunks[j].ev);
+                    cudaEventElapsedTime(&tc, fork, evCatch[j]);
+                    fprintf(stderr, "[dhqr host] chunk at column %5lld: uploaded %7.2f ms, joins at step %2d (planned %2d), caught up %7.2f ms\n",
+                            (long long)c->up_chunks[j].c0, tu, joinedAt[j], c->up_chunks[j].join, tc);
+                }
+                for (int k = K0; k < K; ++k)
+                    fprintf(stderr, "[dhqr host] step %2d: panel %7.2f  T' %7.2f  bulk %7.2f ms\n", k, c->la_times[3 * k], c->la_times[3 * k + 1],
+                            c->la_times[3 * k + 2]);
+            }
         }
     } while (0);
     // error path: the caller's stream must not run ahead of (or return before) work already queued on the internal stream
@@ -919,8 +938,10 @@ static int qr_blocked_lookahead(dhqr_context* c, cudaStream_t st, int64_t m, int
         cudaStreamWaitEvent(st, hpdone, 0);
         cudaEventRecord(hpdone, c->hp2_stream);
         cudaStreamWaitEvent(st, hpdone, 0);
-        cudaEventRecord(hpdone, cu);
-        cudaStreamWaitEvent(st, hpdone, 0);
+        for (int i = 0; i < 3; ++i) {
+            cudaEventRecord(hpdone, c->cu_stream[i]);
+            cudaStreamWaitEvent(st, hpdone, 0);
+        }
         cudaEventDestroy(hpdone);
     }
     for (cudaEvent_t e : evHp)
@@ -1158,7 +1179,7 @@ static int apply_qt_local_vec(dhqr_context* c, cudaStream_t st, int64_t m, int64
         a.V = A + o * lda + cs; a.lda = lda; a.mp = m - cs; a.kb = (int)std::min<int64_t>(NBMAX, nl - o);
         a.b = b + cs; a.Linv = c->qt_T + (size_t)p * NBMAX * NBMAX;
         a.part = c->qt_part; a.y = c->qt_part + (size_t)QT_MAXG * WP; a.ticket = c->qt_ticket; a.trans = notrans;
-        int64_t rpc = rup(std::max<int64_t>((a.mp + 2 * c->sms - 1) / (2 * c->sms), 32), 32);     // two CTAs per SM
+        int64_t rpc = rup(std::max<int64_t>((a.mp + c->sms - 1) / c->sms, 64), 32);                // one CTA per SM
         rpc = std::min<int64_t>(rpc, QT_MAXROWS);
         const int64_t G = (a.mp + rpc - 1) / rpc;
         if (G > QT_MAXG) return set_err(4007, "internal: too many k_qt_dot CTAs");                  // callers check m first
@@ -1167,7 +1188,7 @@ static int apply_qt_local_vec(dhqr_context* c, cudaStream_t st, int64_t m, int64
         k_qt_dot<<<(unsigned)G, QT_THREADS, 0, st>>>(a);
         TRY(post(c, st, "k_qt_dot", 8.0 * (double)a.mp * a.kb));
         pre(c, st);
-        k_qt_axpy<<<(unsigned)((a.mp + QT_THREADS - 1) / QT_THREADS), QT_THREADS, 0, st>>>(a);
+        k_qt_axpy<<<(unsigned)((a.mp + QT_AROWS - 1) / QT_AROWS), QT_ATHREADS, 0, st>>>(a);
         TRY(post(c, st, "k_qt_axpy", 8.0 * (double)a.mp * a.kb));
     }
     return 0;
@@ -1226,7 +1247,7 @@ static int create_common(dhqr_handle* h, int device) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->cu_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) CU(cudaStreamCreateWithFlags(&c->cu_stream[i], cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1276,7 +1297,7 @@ int dhqr_destroy(dhqr_handle c) {
     cudaDeviceSynchronize();
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->linv_all);
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 6; ++b) {
         cudaFree(c->vpk2[b]);
         cudaFree(c->ws[b].wpart); cudaFree(c->ws[b].wsum); cudaFree(c->ws[b].ypk); cudaFree(c->ws[b].linv);
     }
@@ -1295,7 +1316,7 @@ int dhqr_destroy(dhqr_handle c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-    if (c->cu_stream) cudaStreamDestroy(c->cu_stream);
+    for (int i = 0; i < 3; ++i) if (c->cu_stream[i]) cudaStreamDestroy(c->cu_stream[i]);
     delete c;
     return 0;
 }
@@ -1338,6 +1359,12 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "host_h2d_gbs")) {
         if (value < 1) return set_err(-3, "host_h2d_gbs < 1");
         c->host_h2d_gbs = (int)value;
+    } else if (!strcmp(key, "host_chain_us")) {
+        if (value < 1) return set_err(-3, "host_chain_us < 1");
+        c->host_chain_us = (int)value;
+    } else if (!strcmp(key, "host_cu_streams")) {
+        if (value < 1 || value > 3) return set_err(-3, "host_cu_streams must be 1, 2 or 3");
+        c->host_cu_streams = (int)value;
     } else if (!strcmp(key, "host_tflops")) {
         if (value < 1) return set_err(-3, "host_tflops < 1");
         c->host_tflops = (int)value;
@@ -1704,7 +1731,7 @@ static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std
     while (B.back() < n) B.push_back(std::min(n, B.back() + chunk));
     if (n - B[B.size() - 2] < chunk / 2) B.erase(B.end() - 2);           // no sliver at the end
     const int nch = (int)B.size() - 1, K = (int)((n + nb - 1) / nb);
-    const double U = 1e9 * c->host_h2d_gbs, R = 1e12 * c->host_tflops, chain = 0.3e-3;
+    const double U = 1e9 * c->host_h2d_gbs, R = 1e12 * c->host_tflops, chain = 1e-6 * c->host_chain_us;
     auto tup = [&](int j) { return (double)B[j + 1] * (double)m * 8.0 / U; };
     join.assign(nch, 0);
     double T = tup(0);
@@ -1712,8 +1739,7 @@ static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std
     int nxt = 1;
     for (int k = 0; k < K; ++k) {
         while (nxt < nch && (B[nxt] < std::min<int64_t>(n, (int64_t)nb * (k + 4)) || tup(nxt) <= T)) {
-            T = std::max(T, tup(nxt));
-            for (int q = 0; q < k; ++q) T += 4.0 * (double)(m - (int64_t)nb * q) * nb * (double)(B[nxt + 1] - B[nxt]) / R;   // catch-up
+            T = std::max(T, tup(nxt));                        // (the catch-up runs beside the schedule on its own stream)
             join[nxt] = k;
             wend = B[nxt + 1];
             ++nxt;
@@ -1775,7 +1801,7 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
             cudaStreamWaitEvent(c->h2d_stream, e0, 0);
             for (int j = 1; j < nch && !rc; ++j) {
                 cudaEvent_t e;
-                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
+                if (cudaEventCreateWithFlags(&e, c->host_trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) { rc = set_err(1001, "event create failed"); break; }
                 evUp.push_back(e);
                 if (cudaMemcpy2DAsync(dA + B[j] * ldd, (size_t)ldd * 8, hA + B[j] * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(B[j + 1] - B[j]),
                                       cudaMemcpyHostToDevice, c->h2d_stream) != cudaSuccess) { rc = set_err(1001, "H2D failed"); break; }
@@ -1786,7 +1812,10 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
         }
         stamp("first chunk uploaded", true);
         if (blocked) { c->mirror_host = hA; c->mirror_lda = lda; }   // finished panels stream back while later panels are factored
+        const int la_trace_keep = c->la_trace;
+        if (c->host_trace) c->la_trace = 1;
         rc = dhqr_qr_f64(c, m, n, 0, n, dA, ldd, dal, nb, st);
+        c->la_trace = la_trace_keep;
         c->mirror_host = nullptr;
         if (rc) break;
         stamp("factored", true);
@@ -1797,7 +1826,8 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     c->mirror_host = nullptr;
     c->up_chunks.clear();
     cudaError_t e0 = cudaStreamSynchronize(c->h2d_stream), e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->d2h_stream);
-    cudaError_t e3 = cudaStreamSynchronize(c->cu_stream);
+    cudaError_t e3 = cudaSuccess;
+    for (int i = 0; i < 3; ++i) { const cudaError_t e4 = cudaStreamSynchronize(c->cu_stream[i]); if (e3 == cudaSuccess) e3 = e4; }
     stamp("everything back on the host", false);
     for (cudaEvent_t ev : c->panel_events) cudaEventDestroy(ev);
     c->panel_events.clear();

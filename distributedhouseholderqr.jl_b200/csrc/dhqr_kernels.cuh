@@ -1562,8 +1562,10 @@ __global__ void k_pack(const double* __restrict__ A, int64_t lda, int64_t mp, in
 //              y = -T'w (Q'b) or y = -Tw (Qb)
 //   k_qt_axpy: b += V y   (S:156-160 for the whole panel; V comes from L2, the first pass just read it)
 // ------------------------------------------------------------------------------------------------
-constexpr int QT_THREADS = 256;
-constexpr int QT_MAXROWS = 512;            // rows of b a k_qt_dot CTA keeps in shared memory
+constexpr int QT_THREADS = 512;            // k_qt_dot: 16 warps x 8 columns, one CTA per SM
+constexpr int QT_ATHREADS = 256;           // k_qt_axpy: 64 rows x 4 column quarters
+constexpr int QT_AROWS = 64;
+constexpr int QT_MAXROWS = 1024;           // rows of b a k_qt_dot CTA keeps in shared memory
 struct QtArgs {
     const double* V;        // first column of the panel at its pivot row
     int64_t lda;
@@ -1578,40 +1580,51 @@ struct QtArgs {
     int trans;
 };
 
-__global__ void __launch_bounds__(QT_THREADS, 2) k_qt_dot(QtArgs a) {
+__global__ void __launch_bounds__(QT_THREADS, 1) k_qt_dot(QtArgs a) {
     __shared__ double sb[QT_MAXROWS];
-    __shared__ double sw[WP];
+    __shared__ double sw[4][WP];
     __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
     const int nr = (int)max((int64_t)0, min((int64_t)a.rows_per_cta, a.mp - r0));
     for (int r = tid; r < nr; r += QT_THREADS) sb[r] = a.b[r0 + r];
     __syncthreads();
-    // warp w owns columns 16 w .. 16 w + 15; rows r0 + lane + 32 i
-    const int c0 = warp * 16;
-    double acc[16];
+    // warp w owns columns 8 w .. 8 w + 7; lane: rows r0 + lane + 32 i
+    const int c0 = warp * 8;
+    double acc[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
     if (c0 < a.kb) {
         const double* v = a.V + (int64_t)c0 * a.lda + r0;
-        const bool full = (c0 + 16 <= a.kb) && (r0 >= c0 + 15);     // every column live, every row below the diagonal
-        for (int r = lane; r < nr; r += 32) {
-            const double bv = sb[r];
-            if (full) {
+        if ((c0 + 8 <= a.kb) && (r0 >= c0 + 7)) {                    // every column live, every row below the diagonal
+            int r = lane;
+            for (; r + 32 < nr; r += 64) {                            // 16 independent loads in flight per lane
+                const double b0 = sb[r], b1 = sb[r + 32];
+                double x[8], z[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += v[(int64_t)j * a.lda + r] * bv;
-            } else {
+                for (int j = 0; j < 8; ++j) { x[j] = v[(int64_t)j * a.lda + r]; z[j] = v[(int64_t)j * a.lda + r + 32]; }
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < a.kb && r0 + r >= c0 + j) acc[j] += v[(int64_t)j * a.lda + r] * bv;
+                for (int j = 0; j < 8; ++j) acc[j] += x[j] * b0 + z[j] * b1;
+            }
+            for (; r < nr; r += 32) {
+                const double b0 = sb[r];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[(int64_t)j * a.lda + r] * b0;
+            }
+        } else {
+            for (int r = lane; r < nr; r += 32) {
+                const double b0 = sb[r];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < a.kb && r0 + r >= c0 + j) acc[j] += v[(int64_t)j * a.lda + r] * b0;
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a.part[(int64_t)blockIdx.x * WP + c0 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) a.part[(int64_t)blockIdx.x * WP + c0 + j] = acc[j];
     }
     __threadfence();
     __syncthreads();
@@ -1619,43 +1632,76 @@ __global__ void __launch_bounds__(QT_THREADS, 2) k_qt_dot(QtArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < WP) {
-        double s = 0.0;
-        for (unsigned g = 0; g < gridDim.x; ++g) s += __ldcg(&a.part[(int64_t)g * WP + tid]);
-        sw[tid] = s;
+    // the CTA that arrived last: w = sum of the partials in CTA order (four contiguous slices, then a fixed tree), y = -T'w
+    const int c = tid & (WP - 1), sl = tid >> 7;
+    {
+        const int G = (int)gridDim.x, gq = (G + 3) / 4, g0 = sl * gq, g1 = min(G, g0 + gq);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int g = g0;
+        for (; g + 4 <= g1; g += 4) {
+            s0 += __ldcg(&a.part[(int64_t)g * WP + c]);
+            s1 += __ldcg(&a.part[(int64_t)(g + 1) * WP + c]);
+            s2 += __ldcg(&a.part[(int64_t)(g + 2) * WP + c]);
+            s3 += __ldcg(&a.part[(int64_t)(g + 3) * WP + c]);
+        }
+        for (; g < g1; ++g) s0 += __ldcg(&a.part[(int64_t)g * WP + c]);
+        sw[sl][c] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
-    if (tid < WP) {
-        const int i = tid;
-        double s = 0.0;
-        if (!a.trans) for (int k = 0; k <= i; ++k) s += a.Linv[k * WP + i] * sw[k];       // y = -T' w
-        else for (int k = i; k < WP; ++k) s += a.Linv[i * WP + k] * sw[k];                 // y = -T w
-        a.y[i] = -s;
+    if (tid < WP) sb[tid] = (sw[0][tid] + sw[1][tid]) + (sw[2][tid] + sw[3][tid]);
+    __syncthreads();
+    {
+        const int i = c, k0 = sl * 32;
+        double s0 = 0.0, s1 = 0.0;
+        if (!a.trans) {                                               // y = -T' w: row i of the lower triangular T'
+#pragma unroll 8
+            for (int k = k0; k < k0 + 32; k += 2) {
+                if (k <= i) s0 += a.Linv[k * WP + i] * sb[k];
+                if (k + 1 <= i) s1 += a.Linv[(k + 1) * WP + i] * sb[k + 1];
+            }
+        } else {                                                      // y = -T w: column i of T'
+#pragma unroll 8
+            for (int k = k0; k < k0 + 32; k += 2) {
+                if (k >= i) s0 += a.Linv[i * WP + k] * sb[k];
+                if (k + 1 >= i) s1 += a.Linv[i * WP + k + 1] * sb[k + 1];
+            }
+        }
+        sw[sl][i] = s0 + s1;
     }
+    __syncthreads();
+    if (tid < WP) a.y[tid] = -((sw[0][tid] + sw[1][tid]) + (sw[2][tid] + sw[3][tid]));
     if (tid == 0) *a.ticket = 0u;
 }
 
-__global__ void __launch_bounds__(QT_THREADS) k_qt_axpy(QtArgs a) {
+__global__ void __launch_bounds__(QT_ATHREADS) k_qt_axpy(QtArgs a) {
     __shared__ double sy[WP];
-    const int tid = threadIdx.x;
+    __shared__ double sp[4][QT_AROWS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < WP) sy[tid] = a.y[tid];
     __syncthreads();
-    const int64_t r = (int64_t)blockIdx.x * QT_THREADS + tid;
-    if (r >= a.mp) return;
-    const int nc = (int)min((int64_t)a.kb, r + 1);            // columns with row r at or below their diagonal
-    const double* v = a.V + r;
+    const int rl = (warp & 1) * 32 + lane, q = warp >> 1;            // row within the CTA, column quarter
+    const int64_t r = (int64_t)blockIdx.x * QT_AROWS + rl;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = 0;
-    for (; c + 8 <= nc; c += 8) {
-        const double v0 = v[(int64_t)c * a.lda], v1 = v[(int64_t)(c + 1) * a.lda], v2 = v[(int64_t)(c + 2) * a.lda], v3 = v[(int64_t)(c + 3) * a.lda];
-        const double v4 = v[(int64_t)(c + 4) * a.lda], v5 = v[(int64_t)(c + 5) * a.lda], v6 = v[(int64_t)(c + 6) * a.lda], v7 = v[(int64_t)(c + 7) * a.lda];
-        s0 += v0 * sy[c] + v4 * sy[c + 4];
-        s1 += v1 * sy[c + 1] + v5 * sy[c + 5];
-        s2 += v2 * sy[c + 2] + v6 * sy[c + 6];
-        s3 += v3 * sy[c + 3] + v7 * sy[c + 7];
+    if (r < a.mp) {
+        const int c0 = q * 32, c1 = (int)min((int64_t)min(a.kb, c0 + 32), r + 1);   // columns with row r at or below their diagonal
+        const double* v = a.V + r;
+        int c = c0;
+        for (; c + 8 <= c1; c += 8) {
+            const double v0 = v[(int64_t)c * a.lda], v1 = v[(int64_t)(c + 1) * a.lda], v2 = v[(int64_t)(c + 2) * a.lda], v3 = v[(int64_t)(c + 3) * a.lda];
+            const double v4 = v[(int64_t)(c + 4) * a.lda], v5 = v[(int64_t)(c + 5) * a.lda], v6 = v[(int64_t)(c + 6) * a.lda], v7 = v[(int64_t)(c + 7) * a.lda];
+            s0 += v0 * sy[c] + v4 * sy[c + 4];
+            s1 += v1 * sy[c + 1] + v5 * sy[c + 5];
+            s2 += v2 * sy[c + 2] + v6 * sy[c + 6];
+            s3 += v3 * sy[c + 3] + v7 * sy[c + 7];
+        }
+        for (; c < c1; ++c) s0 += v[(int64_t)c * a.lda] * sy[c];
     }
-    for (; c < nc; ++c) s0 += v[(int64_t)c * a.lda] * sy[c];
-    a.b[r] += (s0 + s1) + (s2 + s3);
+    sp[q][rl] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < QT_AROWS) {
+        const int64_t rr = (int64_t)blockIdx.x * QT_AROWS + tid;
+        if (rr < a.mp) a.b[rr] += (sp[0][tid] + sp[1][tid]) + (sp[2][tid] + sp[3][tid]);
+    }
 }
 
 // zero packed columns [c0, c1) over all chunks

@@ -72,6 +72,12 @@ int dhqr_destroy(dhqr_handle h);
  *                 to the column-by-column kernel; 0: always column by column
  *   "panel_ctas"  CTAs of the cooperative panel kernel (0 = default: 64 under look-ahead, one per SM otherwise)
  *   "cvy_warps"   MMA warps per gemm_cvy CTA: 8 (default, 32x32 warp tiles) or 4 (64x32)
+ *   "qt_vec"      1 (default): Q'b / Qb with ONE right-hand side as a GEMV sweep (T' of every panel computed first, then two
+ *                 HBM-bound launches per panel that read the reflectors in place); 0: the GEMM-shaped block update, as for nrhs > 1
+ *   "host_chunk"  columns per upload chunk of dhqr_qr_host_f64 (default 512, a multiple of 128; 0: one upload, no overlap);
+ *                 "host_h2d_gbs" (50), "host_tflops" (27), "host_chain_us" (300): what its join-step planner assumes about the
+ *                 host link, the device and a step of the schedule on a narrow window; "host_cu_streams" (2): catch-up streams;
+ *                 "host_trace" 1: stage timeline on stderr.  A wrong assumption costs idle time, never correctness
  *   "sync"        1: cudaStreamSynchronize + error check after every kernel launch (debugging; implies serial)
  *   "profile"     1: CUDA-event bracket per launch (implies serial), read with dhqr_profile_get
  *   read-only:    "sms", "rank", "nranks", "panels_fast", "panels_fallback" (inner panels taken by either path),
@@ -141,7 +147,11 @@ int dhqr_partialdot_c64(dhqr_handle h, const void *d_a, const void *d_b, int64_t
 
 /* ---- host-buffer entry points (single GPU): the call a CPU-side user of qr! / \ makes -------
  * hA (m x n, lda) is copied to the device, factored, and copied back with alpha; blocks until
- * the result is in host memory.  Pinned host memory makes the copies asynchronous to each other. */
+ * the result is in host memory.  With pinned host memory the call is a pipeline: the matrix goes up in
+ * column chunks, the factorisation starts on the first one, every later chunk joins the trailing matrix
+ * after a catch-up with the reflectors already finished, and finished panels travel back while later
+ * ones are factored; only the first upload and the last download are exposed.  Same reflectors as
+ * dhqr_qr_f64 on the resident matrix (every column receives every reflector once, in order). */
 int dhqr_qr_host_f64(dhqr_handle h, int64_t m, int64_t n, double *hA, int64_t lda, double *h_alpha,
                      int nb);
 /* x = H \ b from a host-resident factorisation (hA, h_alpha) and host b (length m); x length n. */
