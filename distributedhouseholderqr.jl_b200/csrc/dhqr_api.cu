@@ -1160,8 +1160,8 @@ static int qt_prepare(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0,
         K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
         TRY(post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP));
         pre(c, st);
-        k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum + (size_t)p * WP * WP);
-        TRY(post(c, st, "k_wreduce"));
+        k_wreduce4<<<(WP * WP * 4) / 256, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum + (size_t)p * WP * WP);
+        TRY(post(c, st, "k_wreduce4"));
     }
     pre(c, st);
     k_tinv<128><<<npl, 512, smem_tinv(128), st>>>(w.wsum, c->qt_T, (int64_t)WP * WP);

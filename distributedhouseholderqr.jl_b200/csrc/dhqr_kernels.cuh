@@ -285,6 +285,30 @@ __global__ void __launch_bounds__(256) k_wreduce(const double* __restrict__ Wp, 
     }
 }
 
+// wreduce4: the same sum for a SMALL block (a 128 x 128 Gram matrix) where k_wreduce is a chain of nsplit dependent-latency
+// loads per thread: four lanes per element, lane q sums the partials p = q, q+4, ... (ascending), then ((q0+q1)+(q2+q3)).
+// Fixed order -> deterministic (but not the order of k_wreduce).
+__global__ void __launch_bounds__(256) k_wreduce4(const double* __restrict__ Wp, int64_t pstride, int nsplit, int64_t nelem,
+                                                  double* __restrict__ Ws) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t >> 2;
+    const int q = (int)(t & 3);
+    double s = 0.0;
+    if (e < nelem) {
+        int p = q;
+        for (; p + 12 < nsplit; p += 16) {
+            const double v0 = Wp[(int64_t)p * pstride + e], v1 = Wp[(int64_t)(p + 4) * pstride + e];
+            const double v2 = Wp[(int64_t)(p + 8) * pstride + e], v3 = Wp[(int64_t)(p + 12) * pstride + e];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; p < nsplit; p += 4) s += Wp[(int64_t)p * pstride + e];
+    }
+    const double s1 = __shfl_xor_sync(0xffffffffu, s, 1);
+    const double a = (q & 1) ? (s1 + s) : (s + s1);          // lanes 0,1 hold q0 + q1; lanes 2,3 hold q2 + q3
+    const double a2 = __shfl_xor_sync(0xffffffffu, a, 2);
+    if (q == 0 && e < nelem) Ws[e] = a + a2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // gemm_cvy:  C(rows x ncols) += V(rows x nbp) * Y(nbp x ncols)   on rows >= row_lo   ("NN", K = nbp)
 //   Y already carries the minus sign and T' (ymake), so this is A_trail <- (I - V T' V') A_trail.
@@ -1636,16 +1660,15 @@ __global__ void __launch_bounds__(QT_THREADS, 1) k_qt_dot(QtArgs a) {
     const int c = tid & (WP - 1), sl = tid >> 7;
     {
         const int G = (int)gridDim.x, gq = (G + 3) / 4, g0 = sl * gq, g1 = min(G, g0 + gq);
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int g = g0;
-        for (; g + 4 <= g1; g += 4) {
-            s0 += __ldcg(&a.part[(int64_t)g * WP + c]);
-            s1 += __ldcg(&a.part[(int64_t)(g + 1) * WP + c]);
-            s2 += __ldcg(&a.part[(int64_t)(g + 2) * WP + c]);
-            s3 += __ldcg(&a.part[(int64_t)(g + 3) * WP + c]);
+        double s = 0.0;
+        for (int g = g0; g < g1; g += 12) {                          // twelve independent loads in flight, added in CTA order
+            double v[12];
+#pragma unroll
+            for (int u = 0; u < 12; ++u) v[u] = (g + u < g1) ? __ldcg(&a.part[(int64_t)(g + u) * WP + c]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 12; ++u) s += v[u];
         }
-        for (; g < g1; ++g) s0 += __ldcg(&a.part[(int64_t)g * WP + c]);
-        sw[sl][c] = (s0 + s1) + (s2 + s3);
+        sw[sl][c] = s;
     }
     __syncthreads();
     if (tid < WP) sb[tid] = (sw[0][tid] + sw[1][tid]) + (sw[2][tid] + sw[3][tid]);
