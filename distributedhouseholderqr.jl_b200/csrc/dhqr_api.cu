@@ -181,9 +181,10 @@ struct dhqr_context {
     struct UpChunk { int64_t c0, c1; cudaEvent_t ev; int join; };
     std::vector<UpChunk> up_chunks;
     int host_chunk = 512;                    // option: columns per upload chunk (0: one upload, no overlap)
+    int host_first = 0;                      // option: columns of the first upload (0: three panels)
     int host_h2d_gbs = 50, host_tflops = 27; // option: what the join-step planner assumes about the link and the device
     int host_chain_us = 300;                 // option: ... and about the duration of a step of the schedule while the window is narrow
-    int host_cu_streams = 2;                 // option: catch-up streams in use (1..3)
+    int host_cu_streams = 3;                 // option: catch-up streams in use (1..3)
     std::vector<cudaEvent_t> panel_events;
     // set by dhqr_qr_host_f64: finished columns are copied back as soon as their panel is final
     double* mirror_host = nullptr;
@@ -1356,6 +1357,9 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "host_chunk")) {
         if (value < 0 || value % 128) return set_err(-3, "host_chunk must be a non-negative multiple of 128");
         c->host_chunk = (int)value;
+    } else if (!strcmp(key, "host_first")) {
+        if (value < 0) return set_err(-3, "host_first < 0");
+        c->host_first = (int)value;
     } else if (!strcmp(key, "host_h2d_gbs")) {
         if (value < 1) return set_err(-3, "host_h2d_gbs < 1");
         c->host_h2d_gbs = (int)value;
@@ -1725,9 +1729,13 @@ int dhqr_partialdot_c64(dhqr_handle c, const void* d_a, const void* d_b, int64_t
 static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std::vector<int64_t>& B, std::vector<int>& join) {
     B.assign(1, 0);
     join.assign(1, 0);
-    const int64_t chunk = rup(c->host_chunk, nb), first = std::max(rup(chunk + chunk / 2, nb), 3 * (int64_t)nb);   // the schedule starts on panels 0..2
-    if (c->host_chunk <= 0 || m < n || n < first + chunk) { B.push_back(n); return; }
+    // the schedule starts on panels 0..2: the first (exposed) upload is those three panels unless option host_first asks for more;
+    // the second chunk ends where a first chunk of 1.5 chunks would have, so that the later boundaries do not move
+    const int64_t chunk = rup(c->host_chunk, nb), second = std::max(rup(chunk + chunk / 2, nb), 3 * (int64_t)nb);
+    const int64_t first = c->host_first > 0 ? std::min(std::max(rup(c->host_first, nb), 3 * (int64_t)nb), second) : 3 * (int64_t)nb;
+    if (c->host_chunk <= 0 || m < n || n < second + chunk) { B.push_back(n); return; }
     B.push_back(first);
+    if (second > first) B.push_back(second);
     while (B.back() < n) B.push_back(std::min(n, B.back() + chunk));
     if (n - B[B.size() - 2] < chunk / 2) B.erase(B.end() - 2);           // no sliver at the end
     const int nch = (int)B.size() - 1, K = (int)((n + nb - 1) / nb);

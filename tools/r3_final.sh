@@ -11,3 +11,4 @@ timeout 200 python tools/r3_e2e.py quick > gpurun_out/z_e2e.log 2>&1; echo "e2e 
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_qt_dot -s 2 -c 1 -f -o gpurun_out/prof_qtdot python tools/prof_solve.py > gpurun_out/ncu_qtdot.log 2>&1; echo "ncu qt_dot rc=$?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_qt_axpy -s 2 -c 1 -f -o gpurun_out/prof_qtaxpy python tools/prof_solve.py > gpurun_out/ncu_qtaxpy.log 2>&1; echo "ncu qt_axpy rc=$?"
 ls -la gpurun_out/*.ncu-rep
+timeout 200 python tools/r3_plans2.py > gpurun_out/z_plans2.log 2>&1; echo "plans2 rc=$?"; cat gpurun_out/z_plans2.log
