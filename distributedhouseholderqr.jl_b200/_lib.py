@@ -24,6 +24,7 @@ SIGNATURES = {
     "dhqr_launch_count": [_vp, C.POINTER(_i64)],
     "dhqr_profile_reset": [_vp],
     "dhqr_profile_get": [_vp, _int, C.c_char_p, _int, C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_dbl)],
+    "dhqr_plan_host_upload": [_i64, _i64, _int, _int, _int, _int, _int, _int, _int, C.POINTER(_i64), C.POINTER(_int), C.POINTER(_int)],
     "dhqr_qr_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _int, _vp],
     "dhqr_apply_qt_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _int, _vp],
     "dhqr_apply_q_f64": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _int, _vp],

@@ -285,6 +285,20 @@ def _dev_args(A):
     return A, A.shape[1], 0, default_handle(A.device.index)
 
 
+def plan_host_upload(m: int, n: int, nb: int = 128, chunk: int = 512, first: int = 0, h2d_gbs: int = 50, tflops: int = 27,
+                     chain_us: int = 300):
+    """The upload plan of the pipelined host entry (dhqr_plan_host_upload; pure host logic, needs no GPU): (bounds, join) with
+    chunk j = columns [bounds[j], bounds[j+1]) joining the trailing matrix at step join[j] of the look-ahead schedule."""
+    cap = max(2, n // max(nb, 1) + 3)
+    bounds = (C.c_int64 * cap)()
+    join = (C.c_int * cap)()
+    nch = C.c_int()
+    _lib.call("dhqr_plan_host_upload", int(m), int(n), int(nb), int(chunk), int(first), int(h2d_gbs), int(tflops), int(chain_us), cap,
+              bounds, join, C.byref(nch))
+    k = nch.value
+    return [int(bounds[j]) for j in range(k + 1)], [int(join[j]) for j in range(k)]
+
+
 def householder_(A, alpha, nb: int = 0, handle: Optional[Handle] = None):
     """householder!(A, α) (S:113-120): factor in place, α <- diag(R).  Returns (A, α)."""
     loc, n, col0, h = _dev_args(A)

@@ -1726,20 +1726,21 @@ int dhqr_partialdot_c64(dhqr_handle c, const void* d_a, const void* d_b, int64_t
 // the model says it has arrived (earlier = less catch-up work), at the latest one step before the panel chain reaches into it.
 // The model has two parameters (options host_h2d_gbs, host_tflops); a wrong guess costs idle time, never correctness: the
 // driver orders every use of a chunk behind its upload event and forces a join that the plan names too late.
-static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std::vector<int64_t>& B, std::vector<int>& join) {
+struct UploadModel { int chunk, first, h2d_gbs, tflops, chain_us; };
+static void plan_upload(const UploadModel* c, int64_t m, int64_t n, int nb, std::vector<int64_t>& B, std::vector<int>& join) {
     B.assign(1, 0);
     join.assign(1, 0);
     // the schedule starts on panels 0..2: the first (exposed) upload is those three panels unless option host_first asks for more;
     // the second chunk ends where a first chunk of 1.5 chunks would have, so that the later boundaries do not move
-    const int64_t chunk = rup(c->host_chunk, nb), second = std::max(rup(chunk + chunk / 2, nb), 3 * (int64_t)nb);
-    const int64_t first = c->host_first > 0 ? std::min(std::max(rup(c->host_first, nb), 3 * (int64_t)nb), second) : 3 * (int64_t)nb;
-    if (c->host_chunk <= 0 || m < n || n < second + chunk) { B.push_back(n); return; }
+    const int64_t chunk = rup(c->chunk, nb), second = std::max(rup(chunk + chunk / 2, nb), 3 * (int64_t)nb);
+    const int64_t first = c->first > 0 ? std::min(std::max(rup(c->first, nb), 3 * (int64_t)nb), second) : 3 * (int64_t)nb;
+    if (c->chunk <= 0 || m < n || n < second + chunk) { B.push_back(n); return; }
     B.push_back(first);
     if (second > first) B.push_back(second);
     while (B.back() < n) B.push_back(std::min(n, B.back() + chunk));
     if (n - B[B.size() - 2] < chunk / 2) B.erase(B.end() - 2);           // no sliver at the end
     const int nch = (int)B.size() - 1, K = (int)((n + nb - 1) / nb);
-    const double U = 1e9 * c->host_h2d_gbs, R = 1e12 * c->host_tflops, chain = 1e-6 * c->host_chain_us;
+    const double U = 1e9 * c->h2d_gbs, R = 1e12 * c->tflops, chain = 1e-6 * c->chain_us;
     auto tup = [&](int j) { return (double)B[j + 1] * (double)m * 8.0 / U; };
     join.assign(nch, 0);
     double T = tup(0);
@@ -1754,6 +1755,26 @@ static void plan_upload(const dhqr_context* c, int64_t m, int64_t n, int nb, std
         }
         T += std::max(chain, 4.0 * (double)(m - (int64_t)nb * k) * nb * (double)std::max<int64_t>(0, wend - (int64_t)nb * (k + 1)) / R);
     }
+}
+
+int dhqr_plan_host_upload(int64_t m, int64_t n, int nb, int chunk, int first, int h2d_gbs, int tflops, int chain_us, int cap,
+                          int64_t* bounds, int* join, int* nchunks) {
+    if (m < 0) return set_err(-1, "m < 0");
+    if (n < 0 || n > m) return set_err(-2, "need 0 <= n <= m");
+    if (nb < 32 || nb > 128 || nb % 32) return set_err(-3, "nb must be a multiple of 32 in [32,128]");
+    if (chunk < 0 || first < 0) return set_err(chunk < 0 ? -4 : -5, "negative width");
+    if (h2d_gbs < 1 || tflops < 1 || chain_us < 1) return set_err(h2d_gbs < 1 ? -6 : (tflops < 1 ? -7 : -8), "model parameters must be positive");
+    if (!bounds || !join || !nchunks) return set_err(!bounds ? -10 : (!join ? -11 : -12), "null output");
+    const UploadModel um = {chunk, first, h2d_gbs, tflops, chain_us};
+    std::vector<int64_t> B;
+    std::vector<int> J;
+    plan_upload(&um, m, n, nb, B, J);
+    const int nch = (int)B.size() - 1;
+    if (cap < nch + 1) return set_err(-9, "cap too small: %d chunks", nch);
+    for (int j = 0; j <= nch; ++j) bounds[j] = B[j];
+    for (int j = 0; j < nch; ++j) join[j] = J[j];
+    *nchunks = nch;
+    return 0;
 }
 
 int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t lda, double* h_alpha, int nb) {
@@ -1771,7 +1792,8 @@ int dhqr_qr_host_f64(dhqr_handle c, int64_t m, int64_t n, double* hA, int64_t ld
     // stream back while later panels are factored.  One factorisation, the same reflectors as with the matrix resident.
     std::vector<int64_t> B;
     std::vector<int> join;
-    if (blocked) plan_upload(c, m, n, nbe, B, join);
+    const UploadModel um = {c->host_chunk, c->host_first, c->host_h2d_gbs, c->host_tflops, c->host_chain_us};
+    if (blocked) plan_upload(&um, m, n, nbe, B, join);
     else { B = {0, n}; join = {0}; }
     const int nch = (int)B.size() - 1;
     TRY(ensure(&c->hostA, &c->hostA_elems, (size_t)ldd * n + (size_t)n));

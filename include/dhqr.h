@@ -154,6 +154,14 @@ int dhqr_partialdot_c64(dhqr_handle h, const void *d_a, const void *d_b, int64_t
  * dhqr_qr_f64 on the resident matrix (every column receives every reflector once, in order). */
 int dhqr_qr_host_f64(dhqr_handle h, int64_t m, int64_t n, double *hA, int64_t lda, double *h_alpha,
                      int nb);
+/* The upload plan dhqr_qr_host_f64 would use for an m x n matrix with panels of nb columns (pure host logic, needs no device;
+ * exposed for tests and for callers that want to size pinned staging buffers): chunk j = columns [bounds[j], bounds[j+1]),
+ * j < *nchunks; join[j] = step of the look-ahead schedule at which it enters the trailing matrix (join[0] = 0: the first chunk is
+ * the initial window).  Every boundary is a multiple of nb (the last is n); join is non-decreasing and never later than one step
+ * before the panel chain reaches into the chunk (bounds[j] / nb - 3).  chunk, first, h2d_gbs, tflops, chain_us: the options
+ * "host_chunk", "host_first", "host_h2d_gbs", "host_tflops", "host_chain_us".  cap = capacity of bounds (cap) and join (cap - 1). */
+int dhqr_plan_host_upload(int64_t m, int64_t n, int nb, int chunk, int first, int h2d_gbs, int tflops, int chain_us, int cap,
+                          int64_t *bounds, int *join, int *nchunks);
 /* x = H \ b from a host-resident factorisation (hA, h_alpha) and host b (length m); x length n. */
 int dhqr_ldiv_host_f64(dhqr_handle h, int64_t m, int64_t n, const double *hA, int64_t lda,
                        const double *h_alpha, const double *h_b, double *h_x);
