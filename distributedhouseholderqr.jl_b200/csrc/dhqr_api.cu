@@ -165,6 +165,7 @@ struct dhqr_context {
     // Q'b / Qb with one right-hand side: T' of every local panel (computed before the sweep), per-CTA partials of V'b, y, ticket
     double* qt_T = nullptr;  size_t qt_T_elems = 0;
     double* qt_part = nullptr; unsigned int* qt_ticket = nullptr;
+    int gram_sym = 1;                                                   // option: Gram matrices of a packed panel by k_gram_sym (0: k_gemm_vta with the panel as both operands)
     int qt_vec = 1;                                                     // option: use it (0: the GEMM-shaped block update also for one right-hand side)
     double* v1 = nullptr;    size_t v1_elems = 0;                       // unblocked path: v
     double* xbuf = nullptr;  size_t xbuf_elems = 0;                     // back-substitution output
@@ -231,6 +232,7 @@ static int set_attrs(dhqr_context* c) {
     CU(cudaFuncSetAttribute(K_G2D, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g2()));
     CU(cudaFuncSetAttribute(k_gemm_cvy_p, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_gram_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_GRAM_SYM));
     CU(cudaFuncSetAttribute(k_tinv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(128)));
     CU(cudaFuncSetAttribute(k_tinv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tinv(32)));
     CU(cudaFuncSetAttribute(k_ymake<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ymake(128)));
@@ -560,6 +562,33 @@ static int factor_outer_panel_narrow(dhqr_context* c, cudaStream_t st, double* v
     return 0;
 }
 
+// Partial Gram matrices of the packed panel in `vpk` (window rows `rows`) -> w.wpart; returns the number of partials and their stride.
+static int launch_panel_gram(dhqr_context* c, cudaStream_t st, const double* vpk, dhqr_context::WSet& w, int64_t rows, int* nsplit_out,
+                             int64_t* pstride_out) {
+    const int nchunks = (int)((rows + KC1 - 1) / KC1);
+    const int64_t pstride = (int64_t)WP * WP;
+    int nsplit;
+    pre(c, st);
+    if (c->gram_sym) {
+        const int cps = std::max(1, (nchunks + c->sms - 1) / c->sms);                       // chunks per CTA: whole waves of equal CTAs
+        nsplit = (nchunks + cps - 1) / cps;
+        if ((size_t)nsplit * pstride > w.wpart_elems) return set_err(4001, "internal: W partial workspace too small");
+        GramSymArgs g;
+        g.vpk = vpk; g.nchunks = nchunks; g.Wp = w.wpart; g.pstride = pstride;
+        k_gram_sym<<<nsplit, (GS_MMA_WARPS + 1) * 32, SMEM_GRAM_SYM, st>>>(g);
+    } else {
+        const int tiles = WP / G1_BN;
+        nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
+        GemmVtaArgs g1;
+        g1.vpk = vpk; g1.voff = 0; g1.nv = WP; g1.A = vpk; g1.lda = 2; g1.rows = rows; g1.na = 0; g1.nchunks = nchunks;
+        g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
+        K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
+    }
+    *nsplit_out = nsplit;
+    *pstride_out = pstride;
+    return post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP);
+}
+
 // the 128-column chain (dhqr_wide.cuh): CholeskyQR2 + Householder reconstruction of a full aligned outer panel
 static bool wide_eligible(const dhqr_context* c, const Panel& p, int64_t m, int nb) {
     return c->wide_panel && nb == WP && p.kb == WP && (p.c & 31) == 0 && m - p.c >= WP;
@@ -582,26 +611,18 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
         k_vpk_rmul<<<std::min(n, c->sms), 256, SMEM_RMUL, st>>>(r);
         return post(c, st, "k_vpk_rmul", 2.0 * 64.0 * n * WP * 80.0);
     };
-    // Gram matrix of the packed panel: partials of vpk' vpk over the window rows (k_gemm_vta with no trailing columns)
-    const int tiles = WP / G1_BN;
-    const int nchunks = (int)((g.rows + KC1 - 1) / KC1);
-    const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
-    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
-    auto gram = [&]() -> int {
-        GemmVtaArgs g1;
-        g1.vpk = vpk; g1.voff = 0; g1.nv = WP; g1.A = vpk; g1.lda = 2; g1.rows = g.rows; g1.na = 0; g1.nchunks = nchunks;
-        g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
-        pre(c, st);
-        K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
-        return post(c, st, "k_gram128", 2.0 * (double)g.rows * WP * WP);
-    };
+    // Gram matrix of the packed panel: partials of vpk' vpk over the window rows
+    int nsplit = 0;
+    int64_t pstride = 0;
+    auto gram = [&]() -> int { return launch_panel_gram(c, st, vpk, w, g.rows, &nsplit, &pstride); };
     pre(c, st);
     dim3 pgrid((unsigned)std::min<int64_t>((g.vrows / 4 + 255) / 256, 4 * c->sms), WP);
     k_pack<<<pgrid, 256, 0, st>>>(P, lda, g.rows, WP, 0, vpk, 0, 0, g.vrows);
     TRY(post(c, st, "k_pack"));
     TRY(gram());
     pre(c, st);
-    k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
+    if (c->gram_sym) k_wreduce4<<<(WP * WP * 4) / 256, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
+    else k_wreduce<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum);
     TRY(post(c, st, "k_wreduce"));
     pre(c, st);
     k_chol128<<<1, 512, SMEM_WIDE1, st>>>(w.wsum, R1, Z1, c->wctl, step, vflag, c->wide_kappa, stamps);
@@ -609,7 +630,7 @@ static int factor_outer_panel_wide(dhqr_context* c, cudaStream_t st, double* vpk
     TRY(rmul(0, nq, Z1, nullptr));
     TRY(gram());
     pre(c, st);
-    k_gram2_finish<<<64, 256, 0, st>>>(w.wpart, pstride, nsplit, w.wsum, R2, Z2, c->wctl, step, vflag);
+    k_gram2_finish<<<c->gram_sym ? 256 : 64, 256, 0, st>>>(w.wpart, pstride, nsplit, w.wsum, R2, Z2, c->wctl, step, vflag);
     TRY(post(c, st, "k_gram2_finish"));
     // Two small kernels sit beside the chain, not in it (their own high-priority stream, unless the per-launch profile or the
     // debug sync asks for plain stream order): Rt = R2 R1 overlaps the solve of the top chunks, k_trecon the last pass
@@ -1142,8 +1163,6 @@ static int qt_prepare(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0,
     }
     auto& w = c->ws[0];
     if ((size_t)npl * NBMAX * NBMAX > w.wsum_elems) return set_err(4006, "internal: Gram workspace too small");
-    const int tiles = WP / G1_BN;
-    const int64_t pstride = (int64_t)tiles * G1_BN * WP;
     for (int p = 0; p < npl; ++p) {
         const int64_t o = (int64_t)p * NBMAX, cs = col0 + o, r0 = cs & ~(int64_t)31;
         const int kb = (int)std::min<int64_t>(NBMAX, nl - o);
@@ -1152,14 +1171,9 @@ static int qt_prepare(dhqr_context* c, cudaStream_t st, int64_t m, int64_t col0,
         pre(c, st);
         k_pack<<<grid, 256, 0, st>>>(A + o * lda + cs, lda, m - cs, kb, 1, c->vpk2[0], 0, cs - r0, vrows);
         TRY(post(c, st, "k_pack"));
-        const int nchunks = (int)((rows + KC1 - 1) / KC1);
-        const int nsplit = pick_splits(tiles, nchunks, c->sms, 0, (int64_t)(w.wpart_elems / ((size_t)G1_BN * WP)));
-        GemmVtaArgs g1;
-        g1.vpk = c->vpk2[0]; g1.voff = 0; g1.nv = WP; g1.A = c->vpk2[0]; g1.lda = 2; g1.rows = rows; g1.na = 0; g1.nchunks = nchunks;
-        g1.a_aligned = 1; g1.Wp = w.wpart; g1.pstride = pstride;
-        pre(c, st);
-        K_G1_128<<<dim3(tiles, nsplit), (4 * 2 + G1_NPW) * 32, smem_g1(128, G1_BN), st>>>(g1);
-        TRY(post(c, st, "k_gram128", 2.0 * (double)rows * WP * WP));
+        int nsplit = 0;
+        int64_t pstride = 0;
+        TRY(launch_panel_gram(c, st, c->vpk2[0], w, rows, &nsplit, &pstride));
         pre(c, st);
         k_wreduce4<<<(WP * WP * 4) / 256, 256, 0, st>>>(w.wpart, pstride, nsplit, (int64_t)WP * WP, w.wsum + (size_t)p * WP * WP);
         TRY(post(c, st, "k_wreduce4"));
@@ -1244,6 +1258,7 @@ static int create_common(dhqr_handle* h, int device) {
     dhqr_context* c = new dhqr_context();
     c->device = device;
     c->sms = prop.multiProcessorCount;
+    if (const char* e = getenv("DHQR_GRAM_SYM")) c->gram_sym = atoi(e) ? 1 : 0;   // A/B runs of whole test suites (tools/)
     CU(cudaMalloc((void**)&c->d_i64, sizeof(int64_t) * 2 * 1025));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -1372,6 +1387,8 @@ int dhqr_set_option(dhqr_handle c, const char* key, int64_t value) {
     } else if (!strcmp(key, "host_tflops")) {
         if (value < 1) return set_err(-3, "host_tflops < 1");
         c->host_tflops = (int)value;
+    } else if (!strcmp(key, "gram_sym")) {
+        c->gram_sym = value ? 1 : 0;
     } else if (!strcmp(key, "qt_vec")) {
         c->qt_vec = value ? 1 : 0;
     } else if (!strcmp(key, "hp2")) {

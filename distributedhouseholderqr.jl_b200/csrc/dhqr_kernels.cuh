@@ -310,6 +310,96 @@ __global__ void __launch_bounds__(256) k_wreduce4(const double* __restrict__ Wp,
 }
 
 // ------------------------------------------------------------------------------------------------
+// gram_sym:  partial Gram matrices of a packed 128-column panel,  G_s = sum over the CTA's 64-row chunks of Vc' Vc.
+//   k_gemm_vta with the panel as both operands stages every chunk twice (once as V, once as the ext columns of each of its two
+//   column tiles) and computes all 16 32x32 blocks; here a chunk is staged ONCE (one 68 KB bulk copy, 3-stage ring) and only the
+//   10 blocks on or above the diagonal are computed, each by two warps (32 x 16 halves: 20 MMA warps = 5 per scheduler, balanced);
+//   the off-diagonal blocks are written to both triangles, so the partials have the layout the consumers of k_gemm_vta's
+//   partials expect ([split][column][128]).  grid = splits over the chunks; deterministic (fixed chunk order per CTA).
+// ------------------------------------------------------------------------------------------------
+constexpr int GS_STAGES = 3, GS_MMA_WARPS = 20;
+constexpr size_t SMEM_GRAM_SYM = (size_t)GS_STAGES * VPK_CHUNK * 8 + 2 * GS_STAGES * 8;
+struct GramSymArgs {
+    const double* vpk;  // packed panel, window row 0 (rows padded with zeros to whole chunks)
+    int nchunks;        // 64-row chunks to sum over
+    double* Wp;         // partials: [split][128][128]
+    int64_t pstride;
+};
+__global__ void __launch_bounds__((GS_MMA_WARPS + 1) * 32, 1) k_gram_sym(GramSymArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sV = reinterpret_cast<double*>(smem_raw);   // [GS_STAGES][128][LD1]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sV + (size_t)GS_STAGES * VPK_CHUNK);
+    uint64_t* empty = full + GS_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cps = (a.nchunks + gridDim.x - 1) / gridDim.x;
+    const int ch0 = blockIdx.x * cps;
+    const int nit = max(min(ch0 + cps, a.nchunks) - ch0, 0);
+    if (tid == 0) {
+        for (int s = 0; s < GS_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GS_MMA_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == GS_MMA_WARPS) {
+        if (lane == 0) {
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % GS_STAGES;
+                mbar_wait(&empty[s], ((it / GS_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(VPK_CHUNK * 8));
+                bulk_g2s(sV + (size_t)s * VPK_CHUNK, a.vpk + (int64_t)(ch0 + it) * VPK_CHUNK, VPK_CHUNK * 8, &full[s]);
+            }
+        }
+        return;
+    }
+    // warp -> (block row bi, block column bj >= bi, half h of the block's columns)
+    const int blk = warp >> 1, h = warp & 1;
+    int bi = 0, r = blk;
+    while (r >= 4 - bi) { r -= 4 - bi; ++bi; }
+    const int bj = bi + r;
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int frag = (lane >> 2) * LD1 + (lane & 3);
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % GS_STAGES;
+        mbar_wait(&full[s], (it / GS_STAGES) & 1);
+        release_prev_stage(empty, it, GS_STAGES, lane);
+        const double* v = sV + (size_t)s * VPK_CHUNK + bi * 32 * LD1 + frag;
+        const double* b = sV + (size_t)s * VPK_CHUNK + (bj * 32 + h * 16) * LD1 + frag;
+#pragma unroll 4
+        for (int kk = 0; kk < KC1 / 4; ++kk) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = v[i * 8 * LD1 + kk * 4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = b[j * 8 * LD1 + kk * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    double* out = a.Wp + (int64_t)blockIdx.x * a.pstride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = bi * 32 + i * 8 + (lane >> 2);
+            const int col = bj * 32 + h * 16 + j * 8 + (lane & 3) * 2;
+            out[(int64_t)col * VPK_COLS + row] = acc[i][j][0];
+            out[(int64_t)(col + 1) * VPK_COLS + row] = acc[i][j][1];
+            if (bi != bj) {                                            // the mirror image below the diagonal
+                out[(int64_t)row * VPK_COLS + col] = acc[i][j][0];
+                out[(int64_t)row * VPK_COLS + col + 1] = acc[i][j][1];
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gemm_cvy:  C(rows x ncols) += V(rows x nbp) * Y(nbp x ncols)   on rows >= row_lo   ("NN", K = nbp)
 //   Y already carries the minus sign and T' (ymake), so this is A_trail <- (I - V T' V') A_trail.
 //   grid: (row tiles of 128, column tiles of 64); 2 CTAs per SM so one CTA's C-tile load/store

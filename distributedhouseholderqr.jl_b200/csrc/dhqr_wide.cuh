@@ -215,18 +215,37 @@ __global__ void __launch_bounds__(256) k_gram2_finish(const double* __restrict__
                                                       double* __restrict__ Rp, double* __restrict__ ZL, WideCtl* ctl, int step,
                                                       double* vflag) {
     if (wide_gate_closed(ctl, step) || ctl->status) return;
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    if (e >= WP * WP) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = 0;
-    for (; p + 4 <= nsplit; p += 4) {
-        s0 += Wp[(int64_t)p * pstride + e];
-        s1 += Wp[(int64_t)(p + 1) * pstride + e];
-        s2 += Wp[(int64_t)(p + 2) * pstride + e];
-        s3 += Wp[(int64_t)(p + 3) * pstride + e];
+    int e;
+    double g;
+    if (gridDim.x == 64) {                               // one element per thread
+        e = blockIdx.x * 256 + threadIdx.x;
+        if (e >= WP * WP) return;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int p = 0;
+        for (; p + 4 <= nsplit; p += 4) {
+            s0 += Wp[(int64_t)p * pstride + e];
+            s1 += Wp[(int64_t)(p + 1) * pstride + e];
+            s2 += Wp[(int64_t)(p + 2) * pstride + e];
+            s3 += Wp[(int64_t)(p + 3) * pstride + e];
+        }
+        for (; p < nsplit; ++p) s0 += Wp[(int64_t)p * pstride + e];
+        g = (s0 + s1) + (s2 + s3);
+    } else {                                             // grid 256: four lanes per element (the order of k_wreduce4)
+        const int t = blockIdx.x * 256 + threadIdx.x, q = t & 3;
+        e = t >> 2;
+        double s = 0.0;
+        int p = q;
+        for (; p + 12 < nsplit; p += 16) {
+            const double v0 = Wp[(int64_t)p * pstride + e], v1 = Wp[(int64_t)(p + 4) * pstride + e];
+            const double v2 = Wp[(int64_t)(p + 8) * pstride + e], v3 = Wp[(int64_t)(p + 12) * pstride + e];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; p < nsplit; p += 4) s += Wp[(int64_t)p * pstride + e];
+        const double s1 = __shfl_xor_sync(0xffffffffu, s, 1);
+        const double a2 = (q & 1) ? (s1 + s) : (s + s1);
+        g = a2 + __shfl_xor_sync(0xffffffffu, a2, 2);
+        if (q != 0) return;
     }
-    for (; p < nsplit; ++p) s0 += Wp[(int64_t)p * pstride + e];
-    const double g = (s0 + s1) + (s2 + s3);
     Ws[e] = g;
     const int i = e & (WP - 1), j = e >> 7;              // row, column
     const double E = g - (i == j ? 1.0 : 0.0);
