@@ -427,7 +427,26 @@ def run_ours(args):
                 tot_s += dt
         e2e = {"value": flops / (tot_s / Ke) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(sumover(float(m * nl * 8))),
                "d2h_bytes_per_step": int(sumover(float(m * nl * 8))) + n * 8, "ms_per_step": 1e3 * tot_s / Ke, "steps": Ke, "warmup": 2,
-               "path": "dhqr_qr_host_f64 (C-ABI, pinned host buffers)" if world == 1 else "pinned host block -> qr_ -> host (per rank)"}
+               "path": "dhqr_qr_host_f64 (C-ABI, pinned host buffers)" if world == 1 else "pinned host block -> qr_ -> host (per rank)",
+               "input": "pinned host buffer rewritten by the CPU (memcpy from a pageable copy) before every step, outside the timed region"}
+        if world == 1:
+            # The same call when the input sits in DRAM instead of (partly, dirty) in CPU caches - the pinned buffer is refreshed by a
+            # device-to-host copy, as if it had arrived by DMA from a NIC or a disk: DMA reads of lines the CPU has just written are
+            # slower, 3-8 ms per step on this pool's boxes (profiles/r02b_host_pipeline.txt).  Reported next to the headline, not as it.
+            try:
+                import ctypes as C
+                tot2, K2 = 0.0, 4
+                for it in range(1 + K2):
+                    hostA.copy_(src)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    D._lib.call("dhqr_qr_host_f64", h.raw, m, n, C.c_void_p(hostA.data_ptr()), m, C.c_void_p(host_alpha.data_ptr()), nb)
+                    if it >= 1:
+                        tot2 += time.perf_counter() - t0
+                e2e["input_in_dram"] = {"ms_per_step": 1e3 * tot2 / K2, "value": flops / (tot2 / K2) / 1e9, "steps": K2,
+                                        "note": "pinned buffer last written by a device-to-host copy (no dirty CPU cache lines)"}
+            except Exception as ex:
+                e2e["input_in_dram"] = {"error": str(ex)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

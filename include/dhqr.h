@@ -72,6 +72,8 @@ int dhqr_destroy(dhqr_handle h);
  *                 to the column-by-column kernel; 0: always column by column
  *   "panel_ctas"  CTAs of the cooperative panel kernel (0 = default: 64 under look-ahead, one per SM otherwise)
  *   "cvy_warps"   MMA warps per gemm_cvy CTA: 8 (default, 32x32 warp tiles) or 4 (64x32)
+ *   "gram_sym"    1 (default): Gram matrices of a packed 128-column panel by k_gram_sym (chunk staged once, upper blocks only);
+ *                 0: k_gemm_vta with the panel as both operands.  Environment DHQR_GRAM_SYM overrides the default at handle creation
  *   "qt_vec"      1 (default): Q'b / Qb with ONE right-hand side as a GEMV sweep (T' of every panel computed first, then two
  *                 HBM-bound launches per panel that read the reflectors in place); 0: the GEMM-shaped block update, as for nrhs > 1
  *   "host_chunk"  columns per upload chunk of dhqr_qr_host_f64 (default 512, a multiple of 128; 0: one upload, no overlap);
