@@ -113,3 +113,37 @@ def test_bad_arguments():
     assert lib.dhqr_plan_host_upload(4096, 4096, 100, 512, 0, 50, 27, 300, 8, b, j, C.byref(k)) == -3   # nb
     assert lib.dhqr_plan_host_upload(32768, 4096, 128, 512, 0, 50, 27, 300, 4, b, j, C.byref(k)) == -9  # cap
     assert lib.dhqr_plan_host_upload(32768, 4096, 128, 512, 0, 50, 27, 300, 8, None, j, C.byref(k)) == -10
+
+
+def driver_accepts(n, nb, bounds, join):
+    """The join rule of qr_blocked_lookahead without the numerics: True when every chunk joins while it still lies right of
+    panel k+2 and the window always reaches panel k+2 (the driver's internal errors 4005 can then not occur)."""
+    K = (n + nb - 1) // nb
+    wend, nxt = bounds[1], 1
+    for k in range(K):
+        t2, t3 = min(n, (k + 3) * nb), min(n, (k + 4) * nb)
+        while nxt < len(bounds) - 1 and (join[nxt] <= k or bounds[nxt] < t3):
+            if bounds[nxt] < t2 or bounds[nxt] != wend:
+                return False
+            wend = bounds[nxt + 1]
+            nxt += 1
+        if wend < t2:
+            return False
+    return nxt == len(bounds) - 1 and wend == n
+
+
+def test_no_option_setting_can_trip_the_driver():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(nb=st.sampled_from([32, 64, 96, 128]), npan=st.integers(1, 80), ragged=st.integers(0, 127), extra=st.integers(0, 5000),
+           chunk=st.integers(0, 12), first=st.integers(0, 3000), gbs=st.integers(1, 2000), tf=st.integers(1, 200),
+           chain=st.integers(1, 20000))
+    def check(nb, npan, ragged, extra, chunk, first, gbs, tf, chain):
+        n = max(1, npan * nb - (ragged % nb))
+        m = n + extra
+        b, j = D.plan_host_upload(m, n, nb, chunk=128 * chunk, first=first, h2d_gbs=gbs, tflops=tf, chain_us=chain)
+        assert b[0] == 0 and b[-1] == n and len(j) == len(b) - 1
+        assert driver_accepts(n, nb, b, j), (m, n, nb, b, j)
+
+    check()
