@@ -72,6 +72,30 @@ function qr!(A::CuMatrix{Float64}; nb::Integer = 0)
     return H
 end
 
+# ---- qr!(A::Matrix) — a host-resident matrix (S:311 takes any AbstractMatrix): dhqr_qr_host_f64 uploads, factors and downloads
+# inside one call.  With page-locked memory (`pin = true`: CUDA.pin registers the array in place) the call is a pipeline - chunked
+# upload, one factorisation on a growing window, finished panels stream back (DESIGN 2.5); with pageable memory it is still correct.
+function qr!(A::Matrix{Float64}; nb::Integer = 0, pin::Bool = true)
+    m, n = size(A)
+    α = Vector{Float64}(undef, n)
+    pin && (CUDA.pin(A); CUDA.pin(α))
+    GC.@preserve A α check(:dhqr_qr_host_f64, ccall((:dhqr_qr_host_f64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Cint),
+        handle().ptr, m, n, pointer(A), stride(A, 2), pointer(α), nb))
+    return DistributedHouseholderQRStruct(A, α)                                        # H.A === A (S:314)
+end
+# H \ b for that host-resident factorisation (S:317-321): b untouched, x is a new vector
+function LinearAlgebra.:(\)(H::DistributedHouseholderQRStruct{<:Matrix{Float64}}, b0::AbstractVector)
+    m, n = size(H.A)
+    length(b0) == m || throw(DimensionMismatch("b must have length $m"))
+    b = Vector{Float64}(b0)
+    x = Vector{Float64}(undef, n)
+    GC.@preserve H b x check(:dhqr_ldiv_host_f64, ccall((:dhqr_ldiv_host_f64, libdhqr), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        handle().ptr, m, n, pointer(H.A), stride(H.A, 2), pointer(H.α), pointer(b), pointer(x)))
+    return x
+end
+
 # ---- qr!(A::DArray) replaces S:115-119: SPMD call on every owner instead of the sequential owner loop ----
 function local_qr!(A::DArray, n::Int, nb::Integer)
     Al = localpart(A)::CuMatrix{Float64}
